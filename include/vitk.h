@@ -1,0 +1,78 @@
+/*
+ * vitk.h -- C ABI of libvitk.so: hand-written sm_100a (B200) kernels for the ViT encoder hot path of
+ * khuongnd6/ViT_torch (DINO ViT-S/B 16/8, DeiT, CaiT backbones).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers owned by the caller (torch allocates them); the library never allocates
+ *     device memory and keeps no global state except a host-side TMA tensor-map cache guarded by a mutex.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, and returns 0 (VITK_OK)
+ *     or a negative error code. Nothing throws.
+ *   - bf16 matrices are row-major with an explicit leading dimension in ELEMENTS (multiple of 8); fp32 vectors are
+ *     dense. "rows" is always B*N tokens flattened.
+ *   - The reference has no FFI of its own (pure PyTorch): each entry cites the reference Python it replaces
+ *     (paths under the reference tree) and INTEGRATION.md shows the ctypes binding a maintainer would add.
+ */
+#ifndef VITK_H_
+#define VITK_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITK_OK 0
+#define VITK_ERR_ARG (-1)         /* bad shape / alignment / null pointer */
+#define VITK_ERR_UNSUPPORTED (-2) /* combination not compiled in */
+#define VITK_ERR_CUDA (-3)        /* launch failed (cudaGetLastError) */
+#define VITK_ERR_TMAP (-4)        /* cuTensorMapEncodeTiled failed */
+
+/* GEMM epilogues (vitk_gemm_bf16 `epilogue`) */
+#define VITK_EPI_STORE_BF16 0 /* out_bf16 = acc (+bias)                                              */
+#define VITK_EPI_BIAS_GELU 1  /* pre = acc+bias; out_bf16 = pre; out2_bf16 = gelu(pre)   (Mlp.fc1+act) */
+#define VITK_EPI_RESID_F32 2  /* v = acc+bias; [out2_bf16 = v]; out_f32 = resid + gamma*v (proj / fc2)  */
+#define VITK_EPI_DGELU 3      /* out_bf16 = acc * gelu'(aux_bf16)                         (fc2 dgrad)   */
+#define VITK_EPI_ATOMIC_F32 4 /* out_f32 += acc, split-K                                  (wgrad)       */
+#define VITK_EPI_STORE_F32 5  /* out_f32 = acc (+bias)                                                  */
+
+/* Library/ABI version and build info. */
+int vitk_abi_version(void);
+
+/*
+ * D[M,N] = A[M,K] * B[N,K]^T on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM), fused epilogue.
+ *   a_mn_major = 0: A stored [M, lda] (K contiguous);  1: A stored [K, lda] (M contiguous)
+ *   b_mn_major = 0: B stored [N, ldb] (K contiguous);  1: B stored [K, ldb] (N contiguous)
+ * Replaces nn.Linear forward (models/cait.py:99,102,113,126; timm/DINO Attention.qkv/proj, Mlp.fc1/fc2 --
+ * in-repo witness models/swin.py:24-30) and the autograd-generated dgrad (dX = dY W: A=dY, B=W mn-major) and
+ * wgrad (dW = dY^T X: A=dY mn-major, B=X mn-major, VITK_EPI_ATOMIC_F32 accumulating into the fp32 .grad).
+ * N % 8 == 0, lda/ldb % 8 == 0, 16-byte aligned pointers. splits: 0 = auto (only used by VITK_EPI_ATOMIC_F32).
+ */
+int vitk_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major, int M,
+                   int N, int K, int epilogue, const float* bias, const float* gamma, const float* resid,
+                   long long ldr, void* out, long long ldo, void* out2, long long ldo2, const void* aux,
+                   long long ldaux, int splits, void* stream);
+
+/*
+ * LayerNorm forward over the last dim (nn.LayerNorm(D, eps=1e-6): models/cait.py:64,68,203,259; models/deit.py:98).
+ *   x fp32 [rows, D] -> y bf16 [rows, D]; saves mean/rstd fp32 [rows]. D % 4 == 0, D <= 1024.
+ */
+int vitk_layernorm_fwd(const float* x, const float* weight, const float* bias, void* y_bf16, float* mean, float* rstd,
+                       long long rows, int D, float eps, void* stream);
+
+/*
+ * LayerNorm backward fused with the residual-gradient add:
+ *   dx_f32 = dres_f32 (optional) + LN'(dy_bf16);  dx_bf16 (optional) = bf16(dx_f32 * colscale[D] (optional))
+ *   dweight/dbias fp32 [D] are ACCUMULATED (+=) with atomics.
+ */
+int vitk_layernorm_bwd(const void* dy_bf16, const float* x, const float* weight, const float* mean, const float* rstd,
+                       const float* dres, float* dx, void* dx_bf16, const float* colscale, float* dweight,
+                       float* dbias, long long rows, int D, void* stream);
+
+/* Column sums of a bf16 matrix accumulated (+=) into fp32 out[N] (bias gradients: db = sum_rows dY). */
+int vitk_colsum_bf16(const void* x_bf16, long long ldx, long long rows, int N, float* out, void* stream);
+
+/* fp32 -> bf16 cast of n elements (weights, activations). n % 8 == 0 not required. */
+int vitk_cast_f32_bf16(const float* x, void* y_bf16, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITK_H_ */

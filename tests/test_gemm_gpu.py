@@ -1,0 +1,131 @@
+"""tcgen05 GEMM parity (through the C ABI) against torch fp32 matmul on bf16-rounded inputs.
+
+Tolerances: <= 1e-3 normalised max error vs the bf16-rounded-input fp32 oracle for fp32 outputs,
+<= 1e-2 for bf16 outputs (one bf16 rounding of the result: 2^-8 relative).
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def nerr(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def _mk(shape, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(shape, device="cuda", generator=g)
+
+
+SHAPES = [
+    (128, 256, 64), (128, 128, 64), (256, 256, 128), (197 * 8, 768, 768), (1576, 384, 384), (1576, 1152, 384),
+    (25216, 2304, 768), (200, 264, 72), (64, 8, 8), (1000, 3072, 768), (1000, 768, 3072), (130, 48, 200),
+]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_nt_store_f32(M, N, K):
+    from vit_torch_b200 import ops
+    a = _mk((M, K + (-K) % 8), 1)[:, :K].to(torch.bfloat16) if K % 8 else _mk((M, K), 1).to(torch.bfloat16)
+    if K % 8:
+        pytest.skip("K-major operands need K % 8 == 0 (16-byte TMA pitch)")
+    b = _mk((N, K), 2).to(torch.bfloat16)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ops.gemm(a, b, epilogue=ops.EPI_STORE_F32, out=out)
+    ref = a.float() @ b.float().t()
+    e = nerr(out, ref)
+    print(f"NT f32 {M}x{N}x{K}: nerr={e:.3e}")
+    assert e <= 1e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (1576, 384, 1536), (25216, 768, 3072), (333, 768, 2304)])
+def test_gemm_dgrad_layout(M, N, K):
+    """A K-major, B MN-major: dX[M, N] = dY[M, K] @ W[K, N] with W stored row-major [K, N]."""
+    from vit_torch_b200 import ops
+    a = _mk((M, K), 3).to(torch.bfloat16)
+    w = _mk((K, N), 4).to(torch.bfloat16)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ops.gemm(a, w, b_mn=True, epilogue=ops.EPI_STORE_F32, out=out)
+    ref = a.float() @ w.float()
+    e = nerr(out, ref)
+    print(f"dgrad {M}x{N}x{K}: nerr={e:.3e}")
+    assert e <= 1e-3
+
+
+@pytest.mark.parametrize("rows,Nout,Kin,splits", [(256, 256, 128, 1), (1576, 384, 384, 0), (25216, 768, 768, 0),
+                                                  (25216, 3072, 768, 0), (1000, 1152, 384, 3), (777, 128, 64, 0)])
+def test_gemm_wgrad_layout(rows, Nout, Kin, splits):
+    """A and B MN-major, split-K atomic accumulate: dW[Nout, Kin] += dY[rows, Nout]^T @ X[rows, Kin]."""
+    from vit_torch_b200 import ops
+    dy = _mk((rows, Nout), 5).to(torch.bfloat16)
+    x = _mk((rows, Kin), 6).to(torch.bfloat16)
+    init = _mk((Nout, Kin), 7)
+    out = init.clone()
+    ops.gemm(dy, x, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=out, splits=splits)
+    ref = init + dy.float().t() @ x.float()
+    e = nerr(out, ref)
+    print(f"wgrad {rows}: {Nout}x{Kin} splits={splits}: nerr={e:.3e}")
+    assert e <= 1e-3
+
+
+def test_gemm_epilogues():
+    from vit_torch_b200 import ops
+    M, N, K = 1576, 768, 384
+    a = _mk((M, K), 8).to(torch.bfloat16)
+    b = (_mk((N, K), 9) * 0.05).to(torch.bfloat16)
+    bias = _mk((N,), 10)
+    gamma = _mk((N,), 11)
+    resid = _mk((M, N), 12)
+    acc = a.float() @ b.float().t()
+
+    out = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    ops.gemm(a, b, epilogue=ops.EPI_STORE_BF16, bias=bias, out=out)
+    assert nerr(out, acc + bias) <= 1e-2
+
+    pre = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    act = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    ops.gemm(a, b, epilogue=ops.EPI_BIAS_GELU, bias=bias, out=pre, out2=act)
+    assert nerr(pre, acc + bias) <= 1e-2
+    assert nerr(act, torch.nn.functional.gelu(acc + bias)) <= 1e-2
+
+    o32 = torch.empty((M, N), device="cuda")
+    br = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    ops.gemm(a, b, epilogue=ops.EPI_RESID_F32, bias=bias, gamma=gamma, resid=resid, out=o32, out2=br)
+    assert nerr(o32, resid + gamma * (acc + bias)) <= 1e-3
+    assert nerr(br, acc + bias) <= 1e-2
+    o32b = torch.empty((M, N), device="cuda")
+    ops.gemm(a, b, epilogue=ops.EPI_RESID_F32, bias=bias, resid=resid, out=o32b)
+    assert nerr(o32b, resid + acc + bias) <= 1e-3
+
+    # dgelu: out = (dY @ W) * gelu'(aux)
+    w = (_mk((K, N), 13) * 0.05).to(torch.bfloat16)   # [K_red, N] -> B mn-major
+    aux = _mk((M, N), 14).to(torch.bfloat16)
+    dg = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    ops.gemm(a, w, b_mn=True, epilogue=ops.EPI_DGELU, aux=aux, out=dg)
+    xa = aux.float().requires_grad_(True)
+    torch.nn.functional.gelu(xa).sum().backward()
+    assert nerr(dg, (a.float() @ w.float()) * xa.grad) <= 1e-2
+
+
+def test_gemm_strided_views():
+    """Operands and outputs that are column slices of wider buffers (explicit leading dimensions)."""
+    from vit_torch_b200 import ops
+    M, D = 394, 384
+    qkv = _mk((M, 3 * D), 15).to(torch.bfloat16)
+    w = _mk((256, D), 16).to(torch.bfloat16)
+    outbuf = torch.zeros((M, 512), device="cuda")
+    ops.gemm(qkv[:, D:2 * D], w, epilogue=ops.EPI_STORE_F32, out=outbuf[:, 256:])
+    assert nerr(outbuf[:, 256:], qkv[:, D:2 * D].float() @ w.float().t()) <= 1e-3
+    assert outbuf[:, :256].abs().max().item() == 0.0
+
+
+def test_gemm_bad_args_fail_loudly():
+    from vit_torch_b200 import ops, _lib
+    a = torch.zeros((16, 16), dtype=torch.bfloat16, device="cuda")
+    b = torch.zeros((12, 16), dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros((16, 12), device="cuda")
+    with pytest.raises(_lib.VitkError):
+        ops.gemm(a, b, epilogue=ops.EPI_STORE_F32, out=out)   # N % 8 != 0

@@ -1,0 +1,111 @@
+// Host launcher + C-ABI entry for the tcgen05 GEMM (see gemm.cuh for the kernel).
+#include "gemm.cuh"
+#include "tmap.cuh"
+#include "../../include/vitk.h"
+
+namespace vitk {
+
+// Choose the split-K factor for accumulate-epilogue GEMMs (wgrad): minimise waves * k-blocks-per-unit, with a fixed
+// per-unit overhead (pipeline fill + epilogue) expressed in k-block equivalents.
+static int choose_splits(int tiles, int num_kblocks, int sms) {
+    int best = 1;
+    long long best_cost = -1;
+    const int max_s = num_kblocks < 64 ? num_kblocks : 64;
+    for (int s = 1; s <= max_s; ++s) {
+        const int kbps = (num_kblocks + s - 1) / s;
+        const int s_eff = (num_kblocks + kbps - 1) / kbps;
+        const long long units = (long long)tiles * s_eff;
+        const long long waves = (units + sms - 1) / sms;
+        const long long cost = waves * (kbps + 10);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = s_eff;
+        }
+    }
+    return best;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI>;
+    static bool attr_set = false;  // benign race: idempotent
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+            return VITK_ERR_CUDA;
+        attr_set = true;
+    }
+    const int units = g.num_m_tiles * g.num_n_tiles * g.splits;
+    const int grid = units < sm_count() ? units : sm_count();
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
+template <int BN>
+static int dispatch_gemm(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g,
+                         cudaStream_t s) {
+#define VITK_CASE(AM, BM_, E)                                  \
+    if (a_mn == (AM) && b_mn == (BM_) && epi == (E)) return launch_gemm<BN, (AM) != 0, (BM_) != 0, (E)>(tmA, tmB, g, s);
+    // forward Linear: activations K-major, weight [N,K] K-major
+    VITK_CASE(0, 0, EPI_STORE_BF16)
+    VITK_CASE(0, 0, EPI_BIAS_GELU)
+    VITK_CASE(0, 0, EPI_RESID_F32)
+    VITK_CASE(0, 0, EPI_STORE_F32)
+    // dgrad: dY K-major, weight [N_out, K_in] read as MN-major B
+    VITK_CASE(0, 1, EPI_STORE_BF16)
+    VITK_CASE(0, 1, EPI_DGELU)
+    VITK_CASE(0, 1, EPI_STORE_F32)
+    // wgrad: dY^T and X^T, both MN-major, split-K accumulate
+    VITK_CASE(1, 1, EPI_ATOMIC_F32)
+    VITK_CASE(1, 1, EPI_STORE_F32)
+    VITK_CASE(1, 0, EPI_STORE_F32)
+#undef VITK_CASE
+    return VITK_ERR_UNSUPPORTED;
+}
+
+}  // namespace vitk
+
+using namespace vitk;
+
+extern "C" int vitk_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                              int b_mn_major, int M, int N, int K, int epilogue, const float* bias, const float* gamma,
+                              const float* resid, long long ldr, void* out, long long ldo, void* out2, long long ldo2,
+                              const void* aux, long long ldaux, int splits, void* stream) {
+    if (M <= 0 || N <= 0 || K <= 0) return VITK_ERR_ARG;
+    if ((N % 8) != 0 || (lda % 8) != 0 || (ldb % 8) != 0) return VITK_ERR_ARG;
+    if (A == nullptr || B == nullptr || out == nullptr) return VITK_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(out)) & 15)
+        return VITK_ERR_ARG;
+    const int BN = (N % 256 == 0 || N >= 1024) ? 256 : 128;
+
+    GemmArgs g;
+    g.M = M; g.N = N; g.K = K;
+    g.num_m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+    g.num_n_tiles = (N + BN - 1) / BN;
+    g.num_kblocks = (K + GEMM_BK - 1) / GEMM_BK;
+    const bool accumulate = (epilogue == EPI_ATOMIC_F32);
+    int s = 1;
+    if (accumulate) s = splits > 0 ? splits : choose_splits(g.num_m_tiles * g.num_n_tiles, g.num_kblocks, sm_count());
+    if (s > g.num_kblocks) s = g.num_kblocks;
+    g.kblocks_per_split = (g.num_kblocks + s - 1) / s;
+    g.splits = (g.num_kblocks + g.kblocks_per_split - 1) / g.kblocks_per_split;
+    g.bias = bias; g.gamma = gamma; g.resid = resid; g.ldr = ldr;
+    g.out = out; g.ldo = ldo; g.out2 = out2; g.ldo2 = ldo2;
+    g.aux = reinterpret_cast<const __nv_bfloat16*>(aux); g.ldaux = ldaux;
+    if (epilogue == EPI_BIAS_GELU && out2 == nullptr) return VITK_ERR_ARG;
+    if (epilogue == EPI_DGELU && aux == nullptr) return VITK_ERR_ARG;
+
+    CUtensorMap tmA, tmB;
+    int rc;
+    // K-major operand: global [rows, K], box {64 k, rows};  MN-major operand: global [K, rows], box {64 rows, 64 k}
+    if (!a_mn_major) rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM);
+    else             rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, GEMM_BK);
+    if (rc) return VITK_ERR_TMAP;
+    if (!b_mn_major) rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GEMM_BK, (uint32_t)BN);
+    else             rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BK);
+    if (rc) return VITK_ERR_TMAP;
+
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (BN == 256) return dispatch_gemm<256>(a_mn_major != 0, b_mn_major != 0, epilogue, tmA, tmB, g, st);
+    return dispatch_gemm<128>(a_mn_major != 0, b_mn_major != 0, epilogue, tmA, tmB, g, st);
+}

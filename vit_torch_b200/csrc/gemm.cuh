@@ -1,0 +1,290 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:
+//   TMA (128B swizzle) -> shared-memory ring -> tcgen05.mma (UMMA 128 x BN x 16, fp32 accumulators in TMEM,
+//   double-buffered) -> tcgen05.ld epilogue with fused bias / GELU / residual / LayerScale / GELU-grad / split-K.
+//
+//   D[M,N] = A[M,K] * B[N,K]^T            (A and B independently K-major or MN-major in global memory)
+//
+// Replaces on the reference path: nn.Linear forward (models/cait.py:99,102,113,126; timm/DINO Attention.qkv/proj,
+// Mlp.fc1/fc2 -- in-repo witness models/swin.py:24-30) and the autograd dgrad / wgrad of the same Linears.
+//
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
+// warps 4..11 = epilogue (two warps per TMEM lane quarter, each taking half of the BN columns).
+#pragma once
+#include "common.cuh"
+
+namespace vitk {
+
+enum GemmEpilogue : int {
+    EPI_STORE_BF16 = 0,  // out_bf16 = acc (+bias)
+    EPI_BIAS_GELU = 1,   // pre = acc + bias ; out_bf16 = pre ; out2_bf16 = gelu(pre)
+    EPI_RESID_F32 = 2,   // v = acc + bias ; [out2_bf16 = v] ; out_f32 = resid + gamma * v   (gamma optional)
+    EPI_DGELU = 3,       // out_bf16 = acc * gelu'(aux_bf16)
+    EPI_ATOMIC_F32 = 4,  // out_f32 += acc   (red.global.add; split-K wgrad accumulates into the fp32 grad)
+    EPI_STORE_F32 = 5,   // out_f32 = acc (+bias)
+};
+
+struct GemmArgs {
+    int M, N, K;
+    int num_m_tiles, num_n_tiles;
+    int splits, kblocks_per_split, num_kblocks;
+    const float* bias;   // [N] fp32 or null
+    const float* gamma;  // [N] fp32 or null
+    const float* resid;  // fp32 [M, ldr] or null
+    long long ldr;
+    void* out;  // primary output
+    long long ldo;
+    void* out2;  // secondary bf16 output or null
+    long long ldo2;
+    const __nv_bfloat16* aux;  // bf16 [M, ldaux] (EPI_DGELU)
+    long long ldaux;
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_EPI_WARP0 = 4;
+constexpr int GEMM_EPI_WARPS = 8;
+
+template <int BN> struct GemmCfg {
+    static constexpr int A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
+    static constexpr int B_STAGE_BYTES = BN * GEMM_BK * 2;       // 32 KB (BN=256) / 16 KB (BN=128)
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
+};
+
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue_8cols(const GemmArgs& g, const float* acc, long long row, int col) {
+    // acc: 8 fp32 accumulators for columns col..col+7 of one row (row < M, col + 8 <= N guaranteed by caller)
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = acc[i];
+    if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32) {
+        if (g.bias != nullptr) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + col));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + col + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+    }
+    if constexpr (EPI == EPI_STORE_BF16) {
+        uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        st_v4(reinterpret_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col, o);
+    } else if constexpr (EPI == EPI_BIAS_GELU) {
+        uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        st_v4(reinterpret_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col, o);
+        float a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = gelu_f(v[i]);
+        uint4 o2 = make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
+        st_v4(reinterpret_cast<__nv_bfloat16*>(g.out2) + row * g.ldo2 + col, o2);
+    } else if constexpr (EPI == EPI_RESID_F32) {
+        if (g.out2 != nullptr) {
+            uint4 o2 =
+                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            st_v4(reinterpret_cast<__nv_bfloat16*>(g.out2) + row * g.ldo2 + col, o2);
+        }
+        if (g.gamma != nullptr) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(g.gamma + col));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(g.gamma + col + 4));
+            v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
+            v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+        }
+        float* o = reinterpret_cast<float*>(g.out) + row * g.ldo + col;
+        if (g.resid != nullptr) {
+            const float* r = g.resid + row * g.ldr + col;
+            const float4 r0 = *reinterpret_cast<const float4*>(r);
+            const float4 r1 = *reinterpret_cast<const float4*>(r + 4);
+            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+            v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+        }
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else if constexpr (EPI == EPI_DGELU) {
+        const uint4 a = *reinterpret_cast<const uint4*>(g.aux + row * g.ldaux + col);
+        v[0] *= gelu_grad_f(bf16_lo(a.x)); v[1] *= gelu_grad_f(bf16_hi(a.x));
+        v[2] *= gelu_grad_f(bf16_lo(a.y)); v[3] *= gelu_grad_f(bf16_hi(a.y));
+        v[4] *= gelu_grad_f(bf16_lo(a.z)); v[5] *= gelu_grad_f(bf16_hi(a.z));
+        v[6] *= gelu_grad_f(bf16_lo(a.w)); v[7] *= gelu_grad_f(bf16_hi(a.w));
+        uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        st_v4(reinterpret_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col, o);
+    } else if constexpr (EPI == EPI_ATOMIC_F32) {
+        float* o = reinterpret_cast<float*>(g.out) + row * g.ldo + col;
+        red_add_v4_f32(o, v[0], v[1], v[2], v[3]);
+        red_add_v4_f32(o + 4, v[4], v[5], v[6], v[7]);
+    } else if constexpr (EPI == EPI_STORE_F32) {
+        float* o = reinterpret_cast<float*>(g.out) + row * g.ldo + col;
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B operand tiles need 1024 B alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * Cfg::A_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
+    uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]   epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], GEMM_EPI_WARPS);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_units = g.num_m_tiles * g.num_n_tiles * g.splits;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+                const int n_tile = u % g.num_n_tiles;
+                const int rest = u / g.num_n_tiles;
+                const int split = rest % g.splits;
+                const int m_tile = rest / g.splits;
+                const int m0 = m_tile * GEMM_BM, n0 = n_tile * BN;
+                const int kb0 = split * g.kblocks_per_split;
+                const int kb1 = min(kb0 + g.kblocks_per_split, g.num_kblocks);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    uint8_t* sa = smem_a + stage * Cfg::A_STAGE_BYTES;
+                    uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
+                    const int k0 = kb * GEMM_BK;
+                    if constexpr (!A_MN) {
+                        tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);  // box {64 k, 128 m}
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < GEMM_BM / 64; ++j)  // box {64 m, 64 k} per 64-wide M chunk
+                            tma_load_2d(sa + j * (GEMM_BK * 128), &tmA, &full_bar[stage], m0 + 64 * j, k0);
+                    }
+                    if constexpr (!B_MN) {
+                        tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);  // box {64 k, BN n}
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_2d(sb + j * (GEMM_BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, k0);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+            constexpr uint32_t A_LBO = A_MN ? GEMM_BK * 128 : 0, B_LBO = B_MN ? GEMM_BK * 128 : 0;
+            // per-UMMA K advance (16 elements): +32 B inside the 128 B swizzle row (K-major) / +16 rows of 128 B (MN-major)
+            constexpr uint32_t A_KSTEP = (A_MN ? 2048u : 32u) >> 4, B_KSTEP = (B_MN ? 2048u : 32u) >> 4;
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+                const int rest = u / g.num_n_tiles;
+                const int split = rest % g.splits;
+                const int kb0 = split * g.kblocks_per_split;
+                const int kb1 = min(kb0 + g.kblocks_per_split, g.num_kblocks);
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tc_fence_after_sync();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after_sync();
+                    const uint64_t adesc =
+                        make_smem_desc_sw128(smem_u32(smem_a + stage * Cfg::A_STAGE_BYTES), A_LBO, 1024);
+                    const uint64_t bdesc =
+                        make_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES), B_LBO, 1024);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                        umma_bf16(tmem_d, adesc + k * A_KSTEP, bdesc + k * B_KSTEP, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= GEMM_EPI_WARP0) {
+        // ===================== epilogue =====================
+        const int ew = warp - GEMM_EPI_WARP0;
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int half = ew >> 2;      // which half of the BN columns
+        constexpr int COLS_PER_WARP = BN / 2;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+            const int n_tile = u % g.num_n_tiles;
+            const int rest = u / g.num_n_tiles;
+            const int m_tile = rest / g.splits;
+            const long long row = (long long)m_tile * GEMM_BM + quarter * 32 + lane;
+            const int n0 = n_tile * BN + half * COLS_PER_WARP;
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after_sync();
+            const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN + half * COLS_PER_WARP;
+#pragma unroll 1
+            for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(taddr + c * 32, r);
+                tmem_ld_wait();
+                if (c == COLS_PER_WARP / 32 - 1) {
+                    // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[as]);
+                }
+                if (row < g.M) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int col = n0 + c * 32 + q * 8;
+                        if (col + 8 <= g.N)
+                            gemm_epilogue_8cols<EPI>(g, reinterpret_cast<const float*>(r) + q * 8, row, col);
+                    }
+                }
+            }
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after_sync();
+        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+}  // namespace vitk
