@@ -72,6 +72,24 @@ int vitk_colsum_bf16(const void* x_bf16, long long ldx, long long rows, int N, f
 /* fp32 -> bf16 cast of n elements (weights, activations). n % 8 == 0 not required. */
 int vitk_cast_f32_bf16(const float* x, void* y_bf16, long long n, void* stream);
 
+/*
+ * Fused attention forward: out = softmax(q k^T * scale) v per (batch, head); never materialises [B,H,N,N].
+ *   qkv bf16 [B, N, 3, H, d] (the raw qkv Linear output), out bf16 [B, N, H, d] (heads merged, what proj consumes),
+ *   lse2 fp32 [B, H, N] = log2-domain logsumexp of the scaled scores (saved for backward). d in {64, 48}.
+ * Replaces the core of timm/DINO Attention.forward (in-repo witness models/swin.py:119-144).
+ */
+int vitk_attn_fwd(const void* qkv_bf16, void* out_bf16, float* lse2, int B, int N, int H, int d, float scale,
+                  void* stream);
+
+/*
+ * Fused attention backward (recompute): given qkv, the forward output O, dO and lse2, writes dqkv bf16
+ * [B, N, 3, H, d] in place (dQ | dK | dV, the layout the qkv dgrad/wgrad GEMMs consume). delta fp32 [B,H,N] is a
+ * caller-provided scratch (rowsum(dO o O)). Deterministic: no atomics. Autograd of the eager attention in the
+ * reference.
+ */
+int vitk_attn_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2, float* delta,
+                  void* dqkv_bf16, int B, int N, int H, int d, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

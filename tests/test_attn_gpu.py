@@ -1,0 +1,58 @@
+"""Fused attention forward/backward vs the eager fp32 formula, bf16 tolerance 2e-2."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def nerr(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-12)).item()
+
+
+def ref_attn(qkv, B, N, H, d, scale):
+    q, k, v = qkv.float().reshape(B, N, 3, H, d).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-2, -1)) * scale
+    p = s.softmax(-1)
+    o = (p @ v).transpose(1, 2).reshape(B * N, H * d)
+    lse2 = torch.logsumexp(s, -1) / math.log(2.0)
+    return o, lse2
+
+
+CASES = [(2, 197, 6, 64), (1, 128, 1, 64), (3, 37, 2, 64), (2, 785, 3, 64), (2, 196, 8, 48), (1, 145, 12, 64),
+         (1, 1297, 2, 64), (2, 198, 3, 64), (4, 256, 2, 64), (2, 1, 2, 64)]
+
+
+@pytest.mark.parametrize("B,N,H,d", CASES)
+def test_attn_fwd(B, N, H, d):
+    from vit_torch_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + N)
+    qkv = (torch.randn((B * N, 3 * H * d), device="cuda", generator=g) * 1.5).to(torch.bfloat16)
+    scale = d ** -0.5
+    out, lse2 = ops.attn_fwd(qkv, B, N, H, d, scale)
+    ro, rl = ref_attn(qkv, B, N, H, d, scale)
+    e_o, e_l = nerr(out, ro), nerr(lse2, rl)
+    print(f"attn_fwd B{B} N{N} H{H} d{d}: out nerr={e_o:.3e} lse nerr={e_l:.3e}")
+    assert e_o <= 2e-2
+    assert e_l <= 1e-3
+
+
+@pytest.mark.parametrize("B,N,H,d", CASES)
+def test_attn_bwd(B, N, H, d):
+    from vit_torch_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + N + 7)
+    qkv = (torch.randn((B * N, 3 * H * d), device="cuda", generator=g) * 1.2).to(torch.bfloat16)
+    dout = torch.randn((B * N, H * d), device="cuda", generator=g).to(torch.bfloat16)
+    scale = d ** -0.5
+    out, lse2 = ops.attn_fwd(qkv, B, N, H, d, scale)
+    dqkv = ops.attn_bwd(qkv, out, dout, lse2, B, N, H, d, scale)
+    x = qkv.float().requires_grad_(True)
+    ro, _ = ref_attn(x, B, N, H, d, scale)
+    ro.backward(dout.float())
+    ref = x.grad.reshape(B * N, 3, H * d)
+    got = dqkv.float().reshape(B * N, 3, H * d)
+    for i, name in enumerate("qkv"):
+        e = nerr(got[:, i], ref[:, i])
+        print(f"attn_bwd B{B} N{N} H{H} d{d}: d{name} nerr={e:.3e}")
+        assert e <= 2e-2

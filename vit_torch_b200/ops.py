@@ -116,3 +116,30 @@ def cast_bf16(x, out=None):
     check(lib.vitk_cast_f32_bf16(ptr(x), ptr(out), x.numel(), _stream()), "vitk_cast_f32_bf16")
     launch_count += 1
     return out
+
+
+def attn_fwd(qkv, B, N, H, d, scale):
+    """qkv bf16 [B*N, 3*H*d] -> (out bf16 [B*N, H*d], lse2 fp32 [B, H, N])."""
+    global launch_count
+    _need_cuda(qkv)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.numel() == B * N * 3 * H * d
+    out = torch.empty((B * N, H * d), dtype=torch.bfloat16, device=qkv.device)
+    lse2 = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
+    lib = _lib.load()
+    check(lib.vitk_attn_fwd(ptr(qkv), ptr(out), ptr(lse2), B, N, H, d, scale, _stream()), "vitk_attn_fwd")
+    launch_count += 1
+    return out, lse2
+
+
+def attn_bwd(qkv, out, dout, lse2, B, N, H, d, scale):
+    """Returns dqkv bf16 [B*N, 3*H*d] (dQ | dK | dV in the qkv Linear output layout)."""
+    global launch_count
+    _need_cuda(qkv, out, dout, lse2)
+    assert dout.dtype == torch.bfloat16 and dout.is_contiguous() and out.is_contiguous() and qkv.is_contiguous()
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse2)
+    lib = _lib.load()
+    check(lib.vitk_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse2), ptr(delta), ptr(dqkv), B, N, H, d, scale,
+                            _stream()), "vitk_attn_bwd")
+    launch_count += 2
+    return dqkv
