@@ -32,6 +32,7 @@ extern "C" {
 #define VITK_EPI_DGELU 3      /* out_bf16 = acc * gelu'(aux_bf16)                         (fc2 dgrad)   */
 #define VITK_EPI_ATOMIC_F32 4 /* out_f32 += acc, split-K                                  (wgrad)       */
 #define VITK_EPI_STORE_F32 5  /* out_f32 = acc (+bias)                                                  */
+#define VITK_EPI_TOKENS_F32 6 /* PatchEmbed token assembly: row (b,p) -> out_f32[b*tok_N+tok_T+p] = acc+bias+pos[tok_T+p] */
 
 /* Library/ABI version and build info. */
 int vitk_abi_version(void);
@@ -51,6 +52,19 @@ int vitk_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, 
                    long long ldaux, int splits, void* stream);
 
 /*
+ * Same GEMM with the extra epilogue operands:
+ *   rowscale[row / rows_per_sample] multiplies the branch in VITK_EPI_RESID_F32 (DropPath: mask/keep_prob per sample,
+ *   models/cait.py:67,140; identity when null);
+ *   tok_n / tok_N / tok_T drive VITK_EPI_TOKENS_F32 (PatchEmbed + cls/pos assembly: `resid` = pos_embed fp32 [tok_N, ldr],
+ *   models/cait.py:229-233, models/deit.py:35-42, DINO prepare_tokens).
+ */
+int vitk_gemm_bf16_ex(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major, int M,
+                      int N, int K, int epilogue, const float* bias, const float* gamma, const float* resid,
+                      long long ldr, void* out, long long ldo, void* out2, long long ldo2, const void* aux,
+                      long long ldaux, int splits, const float* rowscale, int rows_per_sample, int tok_n, int tok_N,
+                      int tok_T, void* stream);
+
+/*
  * LayerNorm forward over the last dim (nn.LayerNorm(D, eps=1e-6): models/cait.py:64,68,203,259; models/deit.py:98).
  *   x fp32 [rows, D] -> y bf16 [rows, D]; saves mean/rstd fp32 [rows]. D % 4 == 0, D <= 1024.
  */
@@ -65,6 +79,38 @@ int vitk_layernorm_fwd(const float* x, const float* weight, const float* bias, v
 int vitk_layernorm_bwd(const void* dy_bf16, const float* x, const float* weight, const float* mean, const float* rstd,
                        const float* dres, float* dx, void* dx_bf16, const float* colscale, float* dweight,
                        float* dbias, long long rows, int D, void* stream);
+
+/* Strided / fp32-output variants: x rows x_stride elements apart (final norm on the cls rows only: DINO
+ * `norm(x)[:, 0]`, models/cait.py:244-246); y_bf16 and/or y_f32 [rows, D] dense. dy fp32 or bf16 [rows, D] dense;
+ * dres / dx rows dx_stride apart. */
+int vitk_layernorm_fwd_ex(const float* x, long long x_stride, const float* weight, const float* bias, void* y_bf16,
+                          float* y_f32, float* mean, float* rstd, long long rows, int D, float eps, void* stream);
+int vitk_layernorm_bwd_ex(const void* dy, int dy_is_f32, const float* x, long long x_stride, const float* weight,
+                          const float* mean, const float* rstd, const float* dres, float* dx, long long dx_stride,
+                          void* dx_bf16, const float* colscale, float* dweight, float* dbias, long long rows, int D,
+                          void* stream);
+
+/* out[c] += sum_r x[r*ldx + c], fp32 (d_pos = sum_b dX[b,:,:], d_cls; SURVEY App. A.3 token assembly). cols % 4 == 0. */
+int vitk_colsum_f32(const float* x, long long ldx, long long rows, long long cols, float* out, void* stream);
+
+/* out[c] += sum_r a_f32[r,c] * b_bf16[r,c]  (LayerScale d_gamma = sum_rows dY o f; models/cait.py:144-149). */
+int vitk_colsum_prod(const float* a, long long lda, const void* b_bf16, long long ldb, long long rows, int N, float* out,
+                     void* stream);
+
+/* out_bf16[r,:] = bf16(x[(r / rows_per_group) * group_stride + (r % rows_per_group) * D + :] * colscale * rowscale[r / rows_per_sample])
+ * -- the bf16 copy of a residual-stream gradient that the dgrad/wgrad GEMMs read (LayerScale / DropPath folded in),
+ * also used to compact dX[:, T:, :] into patch rows for the PatchEmbed wgrad. D % 8 == 0. */
+int vitk_scale_cast(const float* x, long long rows_per_group, long long group_stride, long long rows, int D,
+                    const float* colscale, const float* rowscale, long long rows_per_sample, void* out_bf16,
+                    void* stream);
+
+/* x fp32 [B,C,H,W] -> bf16 [B*(H/P)*(W/P), C*P*P] patch rows, k = (c,i,j): the A operand of the PatchEmbed GEMM
+ * (Conv2d(C,D,P,P) + flatten(2).transpose(1,2); in-repo analogue models/swin.py:434,445). P % 4 == 0. */
+int vitk_patchify(const float* x, void* out_bf16, int B, int C, int H, int W, int P, void* stream);
+
+/* out[b, t, :] = tok[t,:] + pos[t,:] for the T prefix tokens (cls, dist) of every image. */
+int vitk_prefix_tokens(const float* tok, const float* pos, float* out, int B, int T, long long tokens_per_image, int D,
+                       void* stream);
 
 /* Column sums of a bf16 matrix accumulated (+=) into fp32 out[N] (bias gradients: db = sum_rows dY). */
 int vitk_colsum_bf16(const void* x_bf16, long long ldx, long long rows, int N, float* out, void* stream);

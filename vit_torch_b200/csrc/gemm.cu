@@ -51,6 +51,7 @@ static int dispatch_gemm(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, co
     VITK_CASE(0, 0, EPI_BIAS_GELU)
     VITK_CASE(0, 0, EPI_RESID_F32)
     VITK_CASE(0, 0, EPI_STORE_F32)
+    VITK_CASE(0, 0, EPI_TOKENS_F32)
     // dgrad: dY K-major, weight [N_out, K_in] read as MN-major B
     VITK_CASE(0, 1, EPI_STORE_BF16)
     VITK_CASE(0, 1, EPI_DGELU)
@@ -67,15 +68,19 @@ static int dispatch_gemm(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, co
 
 using namespace vitk;
 
-extern "C" int vitk_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
-                              int b_mn_major, int M, int N, int K, int epilogue, const float* bias, const float* gamma,
-                              const float* resid, long long ldr, void* out, long long ldo, void* out2, long long ldo2,
-                              const void* aux, long long ldaux, int splits, void* stream) {
+static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major, int M,
+                     int N, int K, int epilogue, const float* bias, const float* gamma, const float* resid,
+                     long long ldr, void* out, long long ldo, void* out2, long long ldo2, const void* aux,
+                     long long ldaux, int splits, const float* rowscale, int rows_per_sample, int tok_n, int tok_N,
+                     int tok_T, void* stream) {
     if (M <= 0 || N <= 0 || K <= 0) return VITK_ERR_ARG;
     if ((N % 8) != 0 || (lda % 8) != 0 || (ldb % 8) != 0) return VITK_ERR_ARG;
-    if (A == nullptr || B == nullptr || out == nullptr) return VITK_ERR_ARG;
+    if (A == nullptr || B == nullptr) return VITK_ERR_ARG;
+    if (out == nullptr && !(epilogue == EPI_BIAS_GELU && out2 != nullptr)) return VITK_ERR_ARG;
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(out)) & 15)
         return VITK_ERR_ARG;
+    if (rowscale != nullptr && rows_per_sample <= 0) return VITK_ERR_ARG;
+    if (epilogue == EPI_TOKENS_F32 && (tok_n <= 0 || tok_N < tok_n + tok_T || resid == nullptr)) return VITK_ERR_ARG;
     const int BN = (N % 256 == 0 || N >= 1024) ? 256 : 128;
 
     GemmArgs g;
@@ -92,6 +97,8 @@ extern "C" int vitk_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
     g.bias = bias; g.gamma = gamma; g.resid = resid; g.ldr = ldr;
     g.out = out; g.ldo = ldo; g.out2 = out2; g.ldo2 = ldo2;
     g.aux = reinterpret_cast<const __nv_bfloat16*>(aux); g.ldaux = ldaux;
+    g.rowscale = rowscale; g.rows_per_sample = rows_per_sample;
+    g.tok_n = tok_n; g.tok_N = tok_N; g.tok_T = tok_T;
     if (epilogue == EPI_BIAS_GELU && out2 == nullptr) return VITK_ERR_ARG;
     if (epilogue == EPI_DGELU && aux == nullptr) return VITK_ERR_ARG;
 
@@ -108,4 +115,22 @@ extern "C" int vitk_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (BN == 256) return dispatch_gemm<256>(a_mn_major != 0, b_mn_major != 0, epilogue, tmA, tmB, g, st);
     return dispatch_gemm<128>(a_mn_major != 0, b_mn_major != 0, epilogue, tmA, tmB, g, st);
+}
+
+extern "C" int vitk_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                              int b_mn_major, int M, int N, int K, int epilogue, const float* bias, const float* gamma,
+                              const float* resid, long long ldr, void* out, long long ldo, void* out2, long long ldo2,
+                              const void* aux, long long ldaux, int splits, void* stream) {
+    return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, epilogue, bias, gamma, resid, ldr, out, ldo, out2,
+                     ldo2, aux, ldaux, splits, nullptr, 0, 0, 0, 0, stream);
+}
+
+extern "C" int vitk_gemm_bf16_ex(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                                 int b_mn_major, int M, int N, int K, int epilogue, const float* bias,
+                                 const float* gamma, const float* resid, long long ldr, void* out, long long ldo,
+                                 void* out2, long long ldo2, const void* aux, long long ldaux, int splits,
+                                 const float* rowscale, int rows_per_sample, int tok_n, int tok_N, int tok_T,
+                                 void* stream) {
+    return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, epilogue, bias, gamma, resid, ldr, out, ldo, out2,
+                     ldo2, aux, ldaux, splits, rowscale, rows_per_sample, tok_n, tok_N, tok_T, stream);
 }

@@ -21,6 +21,7 @@ enum GemmEpilogue : int {
     EPI_DGELU = 3,       // out_bf16 = acc * gelu'(aux_bf16)
     EPI_ATOMIC_F32 = 4,  // out_f32 += acc   (red.global.add; split-K wgrad accumulates into the fp32 grad)
     EPI_STORE_F32 = 5,   // out_f32 = acc (+bias)
+    EPI_TOKENS_F32 = 6,  // PatchEmbed: row r = (b, p) -> out_f32[b*tok_N + tok_T + p] = acc + bias + pos[tok_T + p]
 };
 
 struct GemmArgs {
@@ -37,6 +38,9 @@ struct GemmArgs {
     long long ldo2;
     const __nv_bfloat16* aux;  // bf16 [M, ldaux] (EPI_DGELU)
     long long ldaux;
+    const float* rowscale;  // per-sample scale (DropPath mask / keep_prob) indexed by row / rows_per_sample, or null
+    int rows_per_sample;
+    int tok_n, tok_N, tok_T;  // EPI_TOKENS_F32: patches per image, tokens per image, prefix tokens
 };
 
 constexpr int GEMM_BM = 128;
@@ -61,7 +65,8 @@ __device__ __forceinline__ void gemm_epilogue_8cols(const GemmArgs& g, const flo
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = acc[i];
-    if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32) {
+    if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32 ||
+                  EPI == EPI_TOKENS_F32) {
         if (g.bias != nullptr) {
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + col));
             const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + col + 4));
@@ -73,8 +78,11 @@ __device__ __forceinline__ void gemm_epilogue_8cols(const GemmArgs& g, const flo
         uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         st_v4(reinterpret_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col, o);
     } else if constexpr (EPI == EPI_BIAS_GELU) {
-        uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-        st_v4(reinterpret_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col, o);
+        if (g.out != nullptr) {  // pre-activation is only needed for backward
+            uint4 o =
+                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            st_v4(reinterpret_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col, o);
+        }
         float a[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) a[i] = gelu_f(v[i]);
@@ -91,6 +99,11 @@ __device__ __forceinline__ void gemm_epilogue_8cols(const GemmArgs& g, const flo
             const float4 g1 = __ldg(reinterpret_cast<const float4*>(g.gamma + col + 4));
             v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
             v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+        }
+        if (g.rowscale != nullptr) {
+            const float rs = __ldg(g.rowscale + row / g.rows_per_sample);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] *= rs;
         }
         float* o = reinterpret_cast<float*>(g.out) + row * g.ldo + col;
         if (g.resid != nullptr) {
@@ -118,6 +131,15 @@ __device__ __forceinline__ void gemm_epilogue_8cols(const GemmArgs& g, const flo
         float* o = reinterpret_cast<float*>(g.out) + row * g.ldo + col;
         *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else if constexpr (EPI == EPI_TOKENS_F32) {
+        const long long bimg = row / g.tok_n;
+        const int p = static_cast<int>(row - bimg * g.tok_n);
+        const float* pos = g.resid + (long long)(g.tok_T + p) * g.ldr + col;
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(pos));
+        const float4 r1 = __ldg(reinterpret_cast<const float4*>(pos + 4));
+        float* o = reinterpret_cast<float*>(g.out) + (bimg * g.tok_N + g.tok_T + p) * g.ldo + col;
+        *reinterpret_cast<float4*>(o) = make_float4(v[0] + r0.x, v[1] + r0.y, v[2] + r0.z, v[3] + r0.w);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4] + r1.x, v[5] + r1.y, v[6] + r1.z, v[7] + r1.w);
     }
 }
 

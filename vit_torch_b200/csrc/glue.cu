@@ -14,9 +14,9 @@ constexpr int LN_WARPS = 8;
 // ------------------------------------------------------------------------------------------------
 template <int MAXC>
 __global__ void __launch_bounds__(LN_WARPS * 32)
-ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-              __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-              long long rows, int D, float eps) {
+ln_fwd_kernel(const float* __restrict__ x, long long x_stride, const float* __restrict__ w,
+              const float* __restrict__ b, __nv_bfloat16* __restrict__ y, float* __restrict__ y32,
+              float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int D, float eps) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 wv[MAXC], bv[MAXC];
 #pragma unroll
@@ -27,7 +27,7 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
     }
     const float inv_d = 1.0f / static_cast<float>(D);
     for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
-        const float* xr = x + row * D;
+        const float* xr = x + row * x_stride;
         float4 v[MAXC];
         float s = 0.f;
 #pragma unroll
@@ -51,7 +51,6 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
             mean_out[row] = mean;
             rstd_out[row] = rstd;
         }
-        __nv_bfloat16* yr = y + row * D;
 #pragma unroll
         for (int i = 0; i < MAXC; ++i) {
             const int c = (i * 32 + lane) * 4;
@@ -60,7 +59,8 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
                 const float o1 = (v[i].y - mean) * rstd * wv[i].y + bv[i].y;
                 const float o2 = (v[i].z - mean) * rstd * wv[i].z + bv[i].z;
                 const float o3 = (v[i].w - mean) * rstd * wv[i].w + bv[i].w;
-                *reinterpret_cast<uint2*>(yr + c) = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
+                if (y != nullptr) *reinterpret_cast<uint2*>(y + row * D + c) = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
+                if (y32 != nullptr) *reinterpret_cast<float4*>(y32 + row * D + c) = make_float4(o0, o1, o2, o3);
             }
         }
     }
@@ -70,12 +70,13 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
 // LayerNorm backward fused with residual-gradient add and the bf16 copy the next GEMM consumes.
 //   dx = dres + rstd * (dy*w - mean_D(dy*w) - xhat * mean_D(dy*w*xhat));  dw += sum_rows dy*xhat;  db += sum_rows dy
 // ------------------------------------------------------------------------------------------------
-template <int MAXC>
+template <int MAXC, bool DY_F32>
 __global__ void __launch_bounds__(LN_WARPS * 32)
-ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
-              const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dres,
-              float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16, const float* __restrict__ colscale,
-              float* __restrict__ dweight, float* __restrict__ dbias, long long rows, int D) {
+ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long long x_stride,
+              const float* __restrict__ w, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+              const float* __restrict__ dres, float* __restrict__ dx, long long dx_stride,
+              __nv_bfloat16* __restrict__ dx_bf16, const float* __restrict__ colscale, float* __restrict__ dweight,
+              float* __restrict__ dbias, long long rows, int D) {
     __shared__ float red[LN_WARPS * MAXC * 128];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 wv[MAXC], dwa[MAXC], dba[MAXC];
@@ -89,8 +90,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
     const float inv_d = 1.0f / static_cast<float>(D);
     for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
         const float mean = mean_in[row], rstd = rstd_in[row];
-        const float* xr = x + row * D;
-        const __nv_bfloat16* dyr = dy + row * D;
+        const float* xr = x + row * x_stride;
         float4 xh[MAXC], g[MAXC];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -98,8 +98,15 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
             const int c = (i * 32 + lane) * 4;
             if (c < D) {
                 const float4 xv = *reinterpret_cast<const float4*>(xr + c);
-                const uint2 dv = *reinterpret_cast<const uint2*>(dyr + c);
-                const float d0 = bf16_lo(dv.x), d1 = bf16_hi(dv.x), d2 = bf16_lo(dv.y), d3 = bf16_hi(dv.y);
+                float d0, d1, d2, d3;
+                if constexpr (DY_F32) {
+                    const float4 dv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + row * D + c);
+                    d0 = dv.x; d1 = dv.y; d2 = dv.z; d3 = dv.w;
+                } else {
+                    const uint2 dv =
+                        *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy_) + row * D + c);
+                    d0 = bf16_lo(dv.x); d1 = bf16_hi(dv.x); d2 = bf16_lo(dv.y); d3 = bf16_hi(dv.y);
+                }
                 xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd,
                                     (xv.w - mean) * rstd);
                 g[i] = make_float4(d0 * wv[i].x, d1 * wv[i].y, d2 * wv[i].z, d3 * wv[i].w);
@@ -120,10 +127,10 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
                 float4 o = make_float4(rstd * (g[i].x - c1 - xh[i].x * c2), rstd * (g[i].y - c1 - xh[i].y * c2),
                                        rstd * (g[i].z - c1 - xh[i].z * c2), rstd * (g[i].w - c1 - xh[i].w * c2));
                 if (dres != nullptr) {
-                    const float4 r = *reinterpret_cast<const float4*>(dres + row * D + c);
+                    const float4 r = *reinterpret_cast<const float4*>(dres + row * dx_stride + c);
                     o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
                 }
-                if (dx != nullptr) *reinterpret_cast<float4*>(dx + row * D + c) = o;
+                if (dx != nullptr) *reinterpret_cast<float4*>(dx + row * dx_stride + c) = o;
                 if (dx_bf16 != nullptr) {
                     if (colscale != nullptr) {
                         const float4 cs = __ldg(reinterpret_cast<const float4*>(colscale + c));
@@ -197,6 +204,134 @@ cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fp32 column sums with a row stride: out[c] += sum_r x[r*ldx + c]   (d_pos = sum_b dX[b], d_cls)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_f32_kernel(const float* __restrict__ x, long long ldx, long long rows, long long cols, float* __restrict__ out) {
+    const long long c = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (c >= cols) return;
+    float4 acc = make_float4(0, 0, 0, 0);
+    for (long long r = blockIdx.y; r < rows; r += gridDim.y) {
+        const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (gridDim.y == 1) {
+        float4 o = *reinterpret_cast<float4*>(out + c);
+        o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+        *reinterpret_cast<float4*>(out + c) = o;
+    } else {
+        red_add_v4_f32(out + c, acc.x, acc.y, acc.z, acc.w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[c] += sum_r a_f32[r, c] * b_bf16[r, c]     (LayerScale: d_gamma = sum_rows dY o f, models/cait.py:144-149)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_prod_kernel(const float* __restrict__ a, long long lda, const __nv_bfloat16* __restrict__ b, long long ldb,
+                   long long rows, int N, float* __restrict__ out) {
+    __shared__ float red[8][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = blockIdx.x * 256 + lane * 8;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (col + 8 <= N) {
+        for (long long r = (long long)blockIdx.y * 8 + warp; r < rows; r += (long long)gridDim.y * 8) {
+            const uint4 v = ld_nc_v4(b + r * ldb + col);
+            const float4 a0 = *reinterpret_cast<const float4*>(a + r * lda + col);
+            const float4 a1 = *reinterpret_cast<const float4*>(a + r * lda + col + 4);
+            acc[0] += a0.x * bf16_lo(v.x); acc[1] += a0.y * bf16_hi(v.x); acc[2] += a0.z * bf16_lo(v.y);
+            acc[3] += a0.w * bf16_hi(v.y); acc[4] += a1.x * bf16_lo(v.z); acc[5] += a1.y * bf16_hi(v.z);
+            acc[6] += a1.z * bf16_lo(v.w); acc[7] += a1.w * bf16_hi(v.w);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+    __syncthreads();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+        atomicAdd(out + c, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> bf16 with optional per-column / per-sample scale and token-row compaction:
+//   out[r, :] = bf16(x[(r / rpg) * group_stride + (r % rpg) * D + :] * colscale[:] * rowscale[r / rps])
+// (bf16 copy of the residual gradient the dgrad/wgrad GEMMs consume; dX[:, T:, :] -> patch rows for PatchEmbed wgrad)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+scale_cast_kernel(const float* __restrict__ x, long long rpg, long long group_stride, long long rows, int D,
+                  const float* __restrict__ colscale, const float* __restrict__ rowscale, long long rps,
+                  __nv_bfloat16* __restrict__ out) {
+    const int vec_per_row = D / 8;
+    const long long total = rows * vec_per_row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / vec_per_row;
+        const int c = static_cast<int>(i - r * vec_per_row) * 8;
+        const float* src = x + (r / rpg) * group_stride + (r % rpg) * D + c;
+        float4 a = *reinterpret_cast<const float4*>(src);
+        float4 b = *reinterpret_cast<const float4*>(src + 4);
+        if (colscale != nullptr) {
+            const float4 c0 = __ldg(reinterpret_cast<const float4*>(colscale + c));
+            const float4 c1 = __ldg(reinterpret_cast<const float4*>(colscale + c + 4));
+            a.x *= c0.x; a.y *= c0.y; a.z *= c0.z; a.w *= c0.w;
+            b.x *= c1.x; b.y *= c1.y; b.z *= c1.z; b.w *= c1.w;
+        }
+        if (rowscale != nullptr) {
+            const float rs = __ldg(rowscale + r / rps);
+            a.x *= rs; a.y *= rs; a.z *= rs; a.w *= rs;
+            b.x *= rs; b.y *= rs; b.z *= rs; b.w *= rs;
+        }
+        st_v4(out + r * D + c, make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// patchify (v1 of PatchEmbed's A operand): x fp32 [B,C,H,W] -> bf16 [B*n, C*P*P], k = (c, i, j)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C, int H, int W, int P) {
+    const int gw = W / P, gh = H / P;
+    const int K = C * P * P;
+    const int vec_per_row = K / 4;
+    const long long total = (long long)B * gh * gw * vec_per_row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / vec_per_row;
+        const int k = static_cast<int>(i - r * vec_per_row) * 4;
+        const int c = k / (P * P), ij = k - c * P * P, ii = ij / P, jj = ij - ii * P;
+        const int b = static_cast<int>(r / (gh * gw)), p = static_cast<int>(r - (long long)b * gh * gw);
+        const int ph = p / gw, pw = p - ph * gw;
+        const float4 v = *reinterpret_cast<const float4*>(x + (((long long)b * C + c) * H + ph * P + ii) * W + pw * P + jj);
+        *reinterpret_cast<uint2*>(out + r * K + k) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+}
+
+// prefix tokens: out[b, t, :] = tok[t, :] + pos[t, :]  for t < T   (cls / dist tokens; models/deit.py:38-42)
+__global__ void __launch_bounds__(256)
+prefix_tokens_kernel(const float* __restrict__ tok, const float* __restrict__ pos, float* __restrict__ out, int B, int T,
+                     long long tokens_per_image, int D) {
+    const long long total = (long long)B * T * D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = static_cast<int>(i % D);
+        const long long bt = i / D;
+        const int t = static_cast<int>(bt % T);
+        const long long b = bt / T;
+        out[(b * tokens_per_image + t) * D + c] = tok[(long long)t * D + c] + pos[(long long)t * D + c];
+    }
+}
+
+static inline int ew_grid(long long work_items) {
+    long long blocks = (work_items + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
 static inline int ln_grid(long long rows) {
     const long long need = (rows + LN_WARPS - 1) / LN_WARPS;
     const long long cap = (long long)sm_count() * 8;
@@ -207,18 +342,62 @@ static inline int ln_grid(long long rows) {
 
 using namespace vitk;
 
-extern "C" int vitk_layernorm_fwd(const float* x, const float* weight, const float* bias, void* y_bf16, float* mean,
-                                  float* rstd, long long rows, int D, float eps, void* stream) {
-    if (rows <= 0 || D <= 0 || (D % 4) != 0 || D > 1024) return VITK_ERR_ARG;
-    if (!x || !weight || !bias || !y_bf16 || !mean || !rstd) return VITK_ERR_ARG;
+static int ln_fwd_impl(const float* x, long long x_stride, const float* weight, const float* bias, void* y_bf16,
+                       float* y_f32, float* mean, float* rstd, long long rows, int D, float eps, void* stream) {
+    if (rows <= 0 || D <= 0 || (D % 4) != 0 || D > 1024 || (x_stride % 4) != 0) return VITK_ERR_ARG;
+    if (!x || !weight || !bias || (!y_bf16 && !y_f32) || !mean || !rstd) return VITK_ERR_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = ln_grid(rows);
     auto y = reinterpret_cast<__nv_bfloat16*>(y_bf16);
     const int chunks = (D + 127) / 128;
-    if (chunks <= 2) ln_fwd_kernel<2><<<grid, LN_WARPS * 32, 0, st>>>(x, weight, bias, y, mean, rstd, rows, D, eps);
-    else if (chunks <= 3) ln_fwd_kernel<3><<<grid, LN_WARPS * 32, 0, st>>>(x, weight, bias, y, mean, rstd, rows, D, eps);
-    else if (chunks <= 6) ln_fwd_kernel<6><<<grid, LN_WARPS * 32, 0, st>>>(x, weight, bias, y, mean, rstd, rows, D, eps);
-    else ln_fwd_kernel<8><<<grid, LN_WARPS * 32, 0, st>>>(x, weight, bias, y, mean, rstd, rows, D, eps);
+#define VITK_LN_FWD(C) \
+    ln_fwd_kernel<C><<<grid, LN_WARPS * 32, 0, st>>>(x, x_stride, weight, bias, y, y_f32, mean, rstd, rows, D, eps)
+    if (chunks <= 2) VITK_LN_FWD(2);
+    else if (chunks <= 3) VITK_LN_FWD(3);
+    else if (chunks <= 6) VITK_LN_FWD(6);
+    else VITK_LN_FWD(8);
+#undef VITK_LN_FWD
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
+extern "C" int vitk_layernorm_fwd(const float* x, const float* weight, const float* bias, void* y_bf16, float* mean,
+                                  float* rstd, long long rows, int D, float eps, void* stream) {
+    return ln_fwd_impl(x, D, weight, bias, y_bf16, nullptr, mean, rstd, rows, D, eps, stream);
+}
+
+extern "C" int vitk_layernorm_fwd_ex(const float* x, long long x_stride, const float* weight, const float* bias,
+                                     void* y_bf16, float* y_f32, float* mean, float* rstd, long long rows, int D,
+                                     float eps, void* stream) {
+    return ln_fwd_impl(x, x_stride, weight, bias, y_bf16, y_f32, mean, rstd, rows, D, eps, stream);
+}
+
+static int ln_bwd_impl(const void* dy, int dy_is_f32, const float* x, long long x_stride, const float* weight,
+                       const float* mean, const float* rstd, const float* dres, float* dx, long long dx_stride,
+                       void* dx_bf16, const float* colscale, float* dweight, float* dbias, long long rows, int D,
+                       void* stream) {
+    if (rows <= 0 || D <= 0 || (D % 4) != 0 || D > 1024 || (x_stride % 4) != 0 || (dx_stride % 4) != 0)
+        return VITK_ERR_ARG;
+    if (!dy || !x || !weight || !mean || !rstd) return VITK_ERR_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    long long need = (rows + LN_WARPS - 1) / LN_WARPS;
+    const long long cap = (long long)sm_count() * 4;
+    const int grid = (int)(need < cap ? need : cap);
+    auto dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+    const int chunks = (D + 127) / 128;
+#define VITK_LN_BWD(C)                                                                                                \
+    do {                                                                                                              \
+        if (dy_is_f32)                                                                                                \
+            ln_bwd_kernel<C, true><<<grid, LN_WARPS * 32, 0, st>>>(dy, x, x_stride, weight, mean, rstd, dres, dx,     \
+                                                                   dx_stride, dxb, colscale, dweight, dbias, rows, D); \
+        else                                                                                                          \
+            ln_bwd_kernel<C, false><<<grid, LN_WARPS * 32, 0, st>>>(dy, x, x_stride, weight, mean, rstd, dres, dx,    \
+                                                                    dx_stride, dxb, colscale, dweight, dbias, rows, D); \
+    } while (0)
+    if (chunks <= 2) VITK_LN_BWD(2);
+    else if (chunks <= 3) VITK_LN_BWD(3);
+    else if (chunks <= 6) VITK_LN_BWD(6);
+    else VITK_LN_BWD(8);
+#undef VITK_LN_BWD
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
 }
 
@@ -226,24 +405,16 @@ extern "C" int vitk_layernorm_bwd(const void* dy_bf16, const float* x, const flo
                                   const float* rstd, const float* dres, float* dx, void* dx_bf16,
                                   const float* colscale, float* dweight, float* dbias, long long rows, int D,
                                   void* stream) {
-    if (rows <= 0 || D <= 0 || (D % 4) != 0 || D > 1024) return VITK_ERR_ARG;
-    if (!dy_bf16 || !x || !weight || !mean || !rstd) return VITK_ERR_ARG;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    long long need = (rows + LN_WARPS - 1) / LN_WARPS;
-    const long long cap = (long long)sm_count() * 4;
-    const int grid = (int)(need < cap ? need : cap);
-    auto dy = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
-    auto dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
-    const int chunks = (D + 127) / 128;
-#define VITK_LN_BWD(C)                                                                                             \
-    ln_bwd_kernel<C><<<grid, LN_WARPS * 32, 0, st>>>(dy, x, weight, mean, rstd, dres, dx, dxb, colscale, dweight, \
-                                                     dbias, rows, D)
-    if (chunks <= 2) VITK_LN_BWD(2);
-    else if (chunks <= 3) VITK_LN_BWD(3);
-    else if (chunks <= 6) VITK_LN_BWD(6);
-    else VITK_LN_BWD(8);
-#undef VITK_LN_BWD
-    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+    return ln_bwd_impl(dy_bf16, 0, x, D, weight, mean, rstd, dres, dx, D, dx_bf16, colscale, dweight, dbias, rows, D,
+                       stream);
+}
+
+extern "C" int vitk_layernorm_bwd_ex(const void* dy, int dy_is_f32, const float* x, long long x_stride,
+                                     const float* weight, const float* mean, const float* rstd, const float* dres,
+                                     float* dx, long long dx_stride, void* dx_bf16, const float* colscale,
+                                     float* dweight, float* dbias, long long rows, int D, void* stream) {
+    return ln_bwd_impl(dy, dy_is_f32, x, x_stride, weight, mean, rstd, dres, dx, dx_stride, dx_bf16, colscale, dweight,
+                       dbias, rows, D, stream);
 }
 
 extern "C" int vitk_colsum_bf16(const void* x_bf16, long long ldx, long long rows, int N, float* out, void* stream) {
@@ -267,6 +438,61 @@ extern "C" int vitk_cast_f32_bf16(const float* x, void* y_bf16, long long n, voi
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     cast_f32_bf16_kernel<<<(int)blocks, 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(y_bf16), n);
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
+extern "C" int vitk_colsum_f32(const float* x, long long ldx, long long rows, long long cols, float* out, void* stream) {
+    if (rows <= 0 || cols <= 0 || (cols % 4) != 0 || (ldx % 4) != 0 || !x || !out) return VITK_ERR_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long gx = (cols / 4 + 255) / 256;
+    long long gy = (2LL * sm_count() + gx - 1) / gx;
+    if (gy > rows) gy = rows;
+    if (gy < 1) gy = 1;
+    colsum_f32_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, st>>>(x, ldx, rows, cols, out);
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
+extern "C" int vitk_colsum_prod(const float* a, long long lda, const void* b_bf16, long long ldb, long long rows, int N,
+                                float* out, void* stream) {
+    if (rows <= 0 || N <= 0 || (N % 8) != 0 || (lda % 4) != 0 || (ldb % 8) != 0 || !a || !b_bf16 || !out)
+        return VITK_ERR_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int gx = (N + 255) / 256;
+    long long gy = (4LL * sm_count() + gx - 1) / gx;
+    const long long max_gy = (rows + 7) / 8;
+    if (gy > max_gy) gy = max_gy;
+    if (gy < 1) gy = 1;
+    colsum_prod_kernel<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(a, lda, reinterpret_cast<const __nv_bfloat16*>(b_bf16), ldb,
+                                                              rows, N, out);
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
+extern "C" int vitk_scale_cast(const float* x, long long rows_per_group, long long group_stride, long long rows, int D,
+                               const float* colscale, const float* rowscale, long long rows_per_sample, void* out_bf16,
+                               void* stream) {
+    if (rows <= 0 || D <= 0 || (D % 8) != 0 || rows_per_group <= 0 || (group_stride % 4) != 0 || !x || !out_bf16)
+        return VITK_ERR_ARG;
+    if (rowscale != nullptr && rows_per_sample <= 0) return VITK_ERR_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    scale_cast_kernel<<<ew_grid(rows * (D / 8)), 256, 0, st>>>(x, rows_per_group, group_stride, rows, D, colscale, rowscale,
+                                                              rows_per_sample > 0 ? rows_per_sample : 1,
+                                                              reinterpret_cast<__nv_bfloat16*>(out_bf16));
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
+extern "C" int vitk_patchify(const float* x, void* out_bf16, int B, int C, int H, int W, int P, void* stream) {
+    if (B <= 0 || C <= 0 || P <= 0 || (P % 4) != 0 || H % P != 0 || W % P != 0 || !x || !out_bf16) return VITK_ERR_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long total = (long long)B * (H / P) * (W / P) * (C * P * P / 4);
+    patchify_kernel<<<ew_grid(total), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, C, H, W, P);
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
+extern "C" int vitk_prefix_tokens(const float* tok, const float* pos, float* out, int B, int T, long long tokens_per_image,
+                                  int D, void* stream) {
+    if (B <= 0 || T <= 0 || D <= 0 || !tok || !pos || !out) return VITK_ERR_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    prefix_tokens_kernel<<<ew_grid((long long)B * T * D), 256, 0, st>>>(tok, pos, out, B, T, tokens_per_image, D);
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
 }
 

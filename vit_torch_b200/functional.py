@@ -1,0 +1,253 @@
+"""torch.autograd.Functions that sequence the sm_100a kernels for the ViT encoder hot path.
+
+One Function per transformer Block (forward and hand-written backward), one for PatchEmbed + token assembly and one
+for the final LayerNorm on the class token. Numerics policy: fp32 residual stream and fp32 master
+weights / gradients; bf16 GEMM + attention operands and saved activations; fp32 LayerNorm / softmax / GELU math.
+
+Reference semantics: timm/DINO Block, LayerScale_Block (models/cait.py:147-150),
+PatchEmbed + prepare_tokens (models/cait.py:229-234, models/deit.py:35-43), final norm (models/cait.py:242-246).
+"""
+from __future__ import annotations
+
+import weakref
+
+import torch
+
+from . import ops
+
+# ----------------------------------------------------------------------------------------------------------------
+# bf16 weight cache: master weights stay fp32 nn.Parameters; a bf16 copy is refreshed when the parameter changes
+# ----------------------------------------------------------------------------------------------------------------
+_wcache: dict[int, tuple] = {}
+
+
+def bf16_weight(p: torch.Tensor) -> torch.Tensor:
+    """bf16 copy of a 2-D (or conv 4-D, viewed 2-D) fp32 weight, cached on (identity, version, storage)."""
+    key = id(p)
+    ent = _wcache.get(key)
+    ver, dp = p._version, p.data_ptr()
+    if ent is not None and ent[0]() is p and ent[1] == ver and ent[2] == dp:
+        return ent[3]
+    src = p.detach()
+    if not src.is_contiguous():
+        src = src.contiguous()
+    w = ops.cast_bf16(src.view(src.shape[0], -1))
+    _wcache[key] = (weakref.ref(p), ver, dp, w)
+    if len(_wcache) > 4096:
+        for k in [k for k, v in _wcache.items() if v[0]() is None]:
+            del _wcache[k]
+    return w
+
+
+def _flat_grads(params, needs, device):
+    """One contiguous fp32 zero buffer holding the gradients of all params that need one; returns views."""
+    sizes = [p.numel() if (p is not None and need) else 0 for p, need in zip(params, needs)]
+    total = sum(((s + 3) // 4) * 4 for s in sizes)  # keep every view 16-byte aligned
+    buf = torch.zeros((max(total, 4),), dtype=torch.float32, device=device)
+    views, off = [], 0
+    for p, s in zip(params, sizes):
+        if s == 0:
+            views.append(None)
+        else:
+            views.append(buf[off:off + s].view(p.shape))
+            off += ((s + 3) // 4) * 4
+    return buf, views
+
+
+def _dy_bf16(dy2d, M, D, gamma=None, rowscale=None, rows_per_sample=0):
+    """bf16 copy of an fp32 residual-stream gradient (scaled by LayerScale gamma / DropPath), reusing the copy the
+    producing kernel already wrote when there is one."""
+    side = getattr(dy2d, "_vitk_bf16", None)
+    if side is not None and gamma is None and rowscale is None and side.shape == (M, D):
+        return side
+    return ops.scale_cast(dy2d, M, D, colscale=gamma, rowscale=rowscale, rows_per_sample=rows_per_sample)
+
+
+class BlockFn(torch.autograd.Function):
+    """x -> x + g1 * DropPath(Attn(LN1 x)) -> + g2 * DropPath(Mlp(LN2 .)); g1/g2 = None for plain ViT blocks."""
+
+    @staticmethod
+    def forward(ctx, x, num_heads, eps, scale, rowscale, n1w, n1b, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b,
+                fc2w, fc2b, g1, g2):
+        B, N, D = x.shape
+        M = B * N
+        H = num_heads
+        d = D // H
+        x0 = x.contiguous().view(M, D)
+        dev = x.device
+        need_bwd = any(ctx.needs_input_grad)
+        wqkv, wproj, wfc1, wfc2 = bf16_weight(qkvw), bf16_weight(projw), bf16_weight(fc1w), bf16_weight(fc2w)
+        hidden = fc1w.shape[0]
+
+        h1, mean1, rstd1 = ops.layernorm_fwd(x0, n1w, n1b, eps)
+        qkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
+        ops.gemm(h1, wqkv, epilogue=ops.EPI_STORE_BF16, bias=qkvb, out=qkv)
+        o, lse2 = ops.attn_fwd(qkv, B, N, H, d, scale)
+        x1 = torch.empty((M, D), dtype=torch.float32, device=dev)
+        f1 = torch.empty((M, D), dtype=torch.bfloat16, device=dev) if (g1 is not None and need_bwd) else None
+        ops.gemm(o, wproj, epilogue=ops.EPI_RESID_F32, bias=projb, gamma=g1, resid=x0, out=x1, out2=f1,
+                 rowscale=rowscale, rows_per_sample=N)
+        h2, mean2, rstd2 = ops.layernorm_fwd(x1, n2w, n2b, eps)
+        a = torch.empty((M, hidden), dtype=torch.bfloat16, device=dev) if need_bwd else None
+        g = torch.empty((M, hidden), dtype=torch.bfloat16, device=dev)
+        ops.gemm(h2, wfc1, epilogue=ops.EPI_BIAS_GELU, bias=fc1b, out=a, out2=g)
+        x2 = torch.empty((M, D), dtype=torch.float32, device=dev)
+        f2 = torch.empty((M, D), dtype=torch.bfloat16, device=dev) if (g2 is not None and need_bwd) else None
+        ops.gemm(g, wfc2, epilogue=ops.EPI_RESID_F32, bias=fc2b, gamma=g2, resid=x1, out=x2, out2=f2,
+                 rowscale=rowscale, rows_per_sample=N)
+
+        if need_bwd:
+            ctx.save_for_backward(x0, mean1, rstd1, h1, qkv, o, lse2, x1, mean2, rstd2, h2, a, g, f1, f2, n1w, qkvw,
+                                  projw, n2w, fc1w, fc2w, g1, g2, rowscale, wqkv, wproj, wfc1, wfc2)
+            ctx.dims = (B, N, D, H, d, scale)
+            ctx.has = (qkvb is not None, projb is not None, fc1b is not None, fc2b is not None)
+        return x2.view(B, N, D)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x0, mean1, rstd1, h1, qkv, o, lse2, x1, mean2, rstd2, h2, a, g, f1, f2, n1w, qkvw, projw, n2w, fc1w, fc2w,
+         g1, g2, rowscale, wqkv, wproj, wfc1, wfc2) = ctx.saved_tensors
+        B, N, D, H, d, scale = ctx.dims
+        M = B * N
+        dev = dout.device
+        hidden = fc1w.shape[0]
+        needs = ctx.needs_input_grad
+        # parameter order of forward(): index 5.. = n1w n1b qkvw qkvb projw projb n2w n2b fc1w fc1b fc2w fc2b g1 g2
+        shapes_like = [n1w, n1w, qkvw, qkvw[:, 0] if ctx.has[0] else None, projw, projw[:, 0] if ctx.has[1] else None,
+                       n2w, n2w, fc1w, fc1w[:, 0] if ctx.has[2] else None, fc2w, fc2w[:, 0] if ctx.has[3] else None,
+                       g1, g2]
+        buf, gv = _flat_grads(shapes_like, needs[5:19], dev)
+        (dn1w, dn1b, dqkvw, dqkvb, dprojw, dprojb, dn2w, dn2b, dfc1w, dfc1b, dfc2w, dfc2b, dg1, dg2) = gv
+
+        dy = dout if dout.is_contiguous() else dout.contiguous()
+        dx2 = dy.view(M, D)
+        if getattr(dout, "_vitk_bf16", None) is not None:
+            dx2._vitk_bf16 = dout._vitk_bf16
+
+        # ---- Mlp branch: x2 = x1 + g2 * rowscale * (fc2(gelu(fc1(h2))))
+        if dg2 is not None:
+            ops.colsum_prod_accum(dx2, f2, dg2)  # (rowscale == None whenever LayerScale models are built by the zoo)
+        dx2b = _dy_bf16(dx2, M, D, g2, rowscale, N)
+        da = torch.empty((M, hidden), dtype=torch.bfloat16, device=dev)
+        ops.gemm(dx2b, wfc2, b_mn=True, epilogue=ops.EPI_DGELU, aux=a, out=da)
+        if dfc2w is not None:
+            ops.gemm(dx2b, g, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dfc2w)
+        if dfc2b is not None:
+            ops.colsum_accum(dx2b, dfc2b)
+        dh2 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+        ops.gemm(da, wfc1, b_mn=True, epilogue=ops.EPI_STORE_BF16, out=dh2)
+        if dfc1w is not None:
+            ops.gemm(da, h2, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dfc1w)
+        if dfc1b is not None:
+            ops.colsum_accum(da, dfc1b)
+        del da
+        # ---- LN2 backward + residual: dx1 = dx2 + LN2'(dh2); bf16 copy (x g1) feeds the proj dgrad/wgrad
+        plain1 = g1 is None and rowscale is None
+        dx1, dx1b = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dx2, dweight=dn2w, dbias=dn2b, want_bf16=plain1)
+        if dg1 is not None:
+            ops.colsum_prod_accum(dx1, f1, dg1)
+        if not plain1:
+            dx1b = ops.scale_cast(dx1, M, D, colscale=g1, rowscale=rowscale, rows_per_sample=N)
+        # ---- attention branch
+        do = dh2  # reuse the buffer: dO [M, D] bf16
+        ops.gemm(dx1b, wproj, b_mn=True, epilogue=ops.EPI_STORE_BF16, out=do)
+        if dprojw is not None:
+            ops.gemm(dx1b, o, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dprojw)
+        if dprojb is not None:
+            ops.colsum_accum(dx1b, dprojb)
+        dqkv = ops.attn_bwd(qkv, o, do, lse2, B, N, H, d, scale)
+        dh1 = do
+        ops.gemm(dqkv, wqkv, b_mn=True, epilogue=ops.EPI_STORE_BF16, out=dh1)
+        if dqkvw is not None:
+            ops.gemm(dqkv, h1, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dqkvw)
+        if dqkvb is not None:
+            ops.colsum_accum(dqkv, dqkvb)
+        # ---- LN1 backward + residual; the bf16 copy is handed to the previous block through a side channel
+        dx0, dx0b = ops.layernorm_bwd(dh1, x0, n1w, mean1, rstd1, dres=dx1, dweight=dn1w, dbias=dn1b, want_bf16=True)
+        dx = dx0.view(B, N, D)
+        dx._vitk_bf16 = dx0b
+        for hook in grad_bucket_hooks:
+            hook(buf)
+        return (dx, None, None, None, None, dn1w, dn1b, dqkvw, dqkvb, dprojw, dprojb, dn2w, dn2b, dfc1w, dfc1b,
+                dfc2w, dfc2b, dg1, dg2)
+
+
+# callbacks(flat_grad_buffer) fired when one block's parameter gradients are complete (used by dist.py)
+grad_bucket_hooks: list = []
+
+
+class TokensFn(torch.autograd.Function):
+    """PatchEmbed (Conv2d(C,D,P,P) as a patch GEMM) + prefix tokens + positional embedding -> [B, N, D] fp32."""
+
+    @staticmethod
+    def forward(ctx, img, conv_w, conv_b, pos, prefix, patch):
+        B, C, Hh, Ww = img.shape
+        D = conv_w.shape[0]
+        P = patch
+        n = (Hh // P) * (Ww // P)
+        T = 0 if prefix is None else prefix.shape[-2]
+        N = n + T
+        assert pos.shape[-2] == N and pos.shape[-1] == D, f"pos_embed {tuple(pos.shape)} vs tokens {N}x{D}"
+        x = img if img.dtype == torch.float32 else img.float()
+        patches = ops.patchify(x.contiguous(), P)
+        wb = bf16_weight(conv_w)
+        pos2d = pos.detach().reshape(N, D).contiguous()
+        out = torch.empty((B, N, D), dtype=torch.float32, device=img.device)
+        ops.gemm(patches, wb, epilogue=ops.EPI_TOKENS_F32, bias=conv_b, resid=pos2d, out=out.view(B * N, D),
+                 tok=(n, N, T))
+        if T:
+            ops.prefix_tokens(prefix.detach().reshape(T, D).contiguous(), pos2d, out, B, T, N, D)
+        ctx.save_for_backward(patches, conv_w, pos, prefix)
+        ctx.dims = (B, n, N, T, D, conv_b is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        patches, conv_w, pos, prefix = ctx.saved_tensors
+        B, n, N, T, D, has_bias = ctx.dims
+        needs = ctx.needs_input_grad
+        dy = dout if dout.is_contiguous() else dout.contiguous()
+        dev = dy.device
+        dw = db = dpos = dprefix = None
+        if needs[3] or (needs[4] and T):
+            dp = torch.zeros((N * D,), dtype=torch.float32, device=dev)
+            ops.colsum_f32_accum(dy, N * D, B, N * D, dp)
+            if needs[3]:
+                dpos = dp.view(pos.shape)
+            if needs[4] and T:
+                dprefix = dp[:T * D].clone().view(prefix.shape)
+        if needs[1] or (needs[2] and has_bias):
+            dyb = ops.scale_cast(dy, B * n, D, rows_per_group=n, group_stride=N * D, offset_elems=T * D)
+            if needs[1]:
+                dw = torch.zeros(conv_w.shape, dtype=torch.float32, device=dev)
+                ops.gemm(dyb, patches, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dw.view(D, -1))
+            if needs[2] and has_bias:
+                db = torch.zeros((D,), dtype=torch.float32, device=dev)
+                ops.colsum_accum(dyb, db)
+        return None, dw, db, dpos, dprefix, None
+
+
+class TokenNormFn(torch.autograd.Function):
+    """LayerNorm of one token (index `tok`) of every image: x [B, N, D] fp32 -> [B, D] fp32 (norm(x)[:, tok])."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps, tok):
+        B, N, D = x.shape
+        xc = x if x.is_contiguous() else x.contiguous()
+        xv = xc.view(-1)[tok * D:]
+        y, mean, rstd = ops.layernorm_fwd_rows(xv, N * D, B, D, w, b, eps, out_f32=True)
+        ctx.save_for_backward(xc, w, mean, rstd)
+        ctx.dims = (B, N, D, tok)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, w, mean, rstd = ctx.saved_tensors
+        B, N, D, tok = ctx.dims
+        dy = dy.contiguous().float()
+        dx = torch.zeros((B, N, D), dtype=torch.float32, device=dy.device)
+        dw = torch.zeros((D,), dtype=torch.float32, device=dy.device)
+        db = torch.zeros((D,), dtype=torch.float32, device=dy.device)
+        ops.layernorm_bwd_rows(dy, xc.view(-1)[tok * D:], N * D, B, D, w, mean, rstd, dx=dx.view(-1)[tok * D:],
+                               dx_stride=N * D, dweight=dw, dbias=db)
+        return dx, dw, db, None, None

@@ -36,8 +36,11 @@ def _ld(t: torch.Tensor) -> int:
     return t.stride(0)
 
 
+EPI_TOKENS_F32 = 6
+
+
 def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, epilogue=EPI_STORE_BF16, bias=None, gamma=None,
-         resid=None, out=None, out2=None, aux=None, splits=0):
+         resid=None, out=None, out2=None, aux=None, splits=0, rowscale=None, rows_per_sample=0, tok=None):
     """D[M,N] = A[M,K] @ B[N,K]^T with a fused epilogue. See vitk_gemm_bf16 in include/vitk.h.
 
     a: bf16 [M,K] (a_mn=False) or [K,M] (a_mn=True); b: bf16 [N,K] (b_mn=False) or [K,N] (b_mn=True).
@@ -52,12 +55,14 @@ def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, epilogue=EPI_S
     if N is None:
         N = b.shape[1] if b_mn else b.shape[0]
     lib = _lib.load()
-    rc = lib.vitk_gemm_bf16(
+    tok_n, tok_N, tok_T = tok if tok is not None else (0, 0, 0)
+    rc = lib.vitk_gemm_bf16_ex(
         ptr(a), _ld(a), int(a_mn), ptr(b), _ld(b), int(b_mn), M, N, K, epilogue,
         ptr(bias), ptr(gamma), ptr(resid), _ld(resid) if resid is not None else 0,
-        ptr(out), _ld(out), ptr(out2), _ld(out2) if out2 is not None else 0,
-        ptr(aux), _ld(aux) if aux is not None else 0, splits, _stream())
-    check(rc, "vitk_gemm_bf16")
+        ptr(out), _ld(out) if out is not None else 0, ptr(out2), _ld(out2) if out2 is not None else 0,
+        ptr(aux), _ld(aux) if aux is not None else 0, splits, ptr(rowscale), rows_per_sample, tok_n, tok_N, tok_T,
+        _stream())
+    check(rc, "vitk_gemm_bf16_ex")
     launch_count += 1
     return out
 
@@ -143,3 +148,93 @@ def attn_bwd(qkv, out, dout, lse2, B, N, H, d, scale):
                             _stream()), "vitk_attn_bwd")
     launch_count += 2
     return dqkv
+
+
+def layernorm_fwd_rows(x, x_stride, rows, D, weight, bias, eps=1e-6, out_f32=False):
+    """LayerNorm over `rows` rows of width D spaced x_stride elements apart in fp32 tensor x.
+    Returns (y [rows, D] bf16 or fp32, mean, rstd)."""
+    global launch_count
+    _need_cuda(x, weight, bias)
+    assert x.dtype == torch.float32
+    y = torch.empty((rows, D), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    mean = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    rstd = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    check(lib.vitk_layernorm_fwd_ex(ptr(x), x_stride, ptr(weight), ptr(bias), None if out_f32 else ptr(y),
+                                    ptr(y) if out_f32 else None, ptr(mean), ptr(rstd), rows, D, eps, _stream()),
+          "vitk_layernorm_fwd_ex")
+    launch_count += 1
+    return y, mean, rstd
+
+
+def layernorm_bwd_rows(dy, x, x_stride, rows, D, weight, mean, rstd, *, dres=None, dx=None, dx_stride=None,
+                       dx_bf16=None, colscale=None, dweight=None, dbias=None):
+    """Strided LayerNorm backward; dy dense [rows, D] fp32 or bf16; writes dx (fp32, rows dx_stride apart) in place."""
+    global launch_count
+    _need_cuda(dy, x)
+    assert dy.is_contiguous() and dy.dtype in (torch.float32, torch.bfloat16)
+    lib = _lib.load()
+    check(lib.vitk_layernorm_bwd_ex(ptr(dy), int(dy.dtype == torch.float32), ptr(x), x_stride, ptr(weight), ptr(mean),
+                                    ptr(rstd), ptr(dres), ptr(dx), dx_stride if dx_stride is not None else D,
+                                    ptr(dx_bf16), ptr(colscale), ptr(dweight), ptr(dbias), rows, D, _stream()),
+          "vitk_layernorm_bwd_ex")
+    launch_count += 1
+
+
+def colsum_f32_accum(x, ldx, rows, cols, out):
+    """out[c] (fp32) += sum_r x[r*ldx + c]."""
+    global launch_count
+    _need_cuda(x, out)
+    lib = _lib.load()
+    check(lib.vitk_colsum_f32(ptr(x), ldx, rows, cols, ptr(out), _stream()), "vitk_colsum_f32")
+    launch_count += 1
+
+
+def colsum_prod_accum(a, b, out):
+    """out[N] += sum_r a_f32[r, :] * b_bf16[r, :]."""
+    global launch_count
+    _need_cuda(a, b, out)
+    assert a.dtype == torch.float32 and b.dtype == torch.bfloat16
+    lib = _lib.load()
+    check(lib.vitk_colsum_prod(ptr(a), _ld(a), ptr(b), _ld(b), a.shape[0], a.shape[1], ptr(out), _stream()),
+          "vitk_colsum_prod")
+    launch_count += 1
+
+
+def scale_cast(x, rows, D, *, rows_per_group=None, group_stride=0, colscale=None, rowscale=None, rows_per_sample=0,
+               offset_elems=0):
+    """bf16 [rows, D] = x (fp32) * colscale * rowscale with optional token-row compaction (see vitk_scale_cast)."""
+    global launch_count
+    _need_cuda(x)
+    assert x.dtype == torch.float32
+    out = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device)
+    if rows_per_group is None:
+        rows_per_group, group_stride = rows, 0
+    lib = _lib.load()
+    check(lib.vitk_scale_cast(x.data_ptr() + 4 * offset_elems, rows_per_group, group_stride, rows, D, ptr(colscale),
+                              ptr(rowscale), rows_per_sample, ptr(out), _stream()), "vitk_scale_cast")
+    launch_count += 1
+    return out
+
+
+def patchify(x, P):
+    """x fp32 [B,C,H,W] -> bf16 [B*(H/P)*(W/P), C*P*P]."""
+    global launch_count
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    B, C, H, W = x.shape
+    out = torch.empty((B * (H // P) * (W // P), C * P * P), dtype=torch.bfloat16, device=x.device)
+    lib = _lib.load()
+    check(lib.vitk_patchify(ptr(x), ptr(out), B, C, H, W, P, _stream()), "vitk_patchify")
+    launch_count += 1
+    return out
+
+
+def prefix_tokens(tok, pos, out, B, T, tokens_per_image, D):
+    """out[b, t, :] = tok[t] + pos[t] for t < T."""
+    global launch_count
+    _need_cuda(tok, pos, out)
+    lib = _lib.load()
+    check(lib.vitk_prefix_tokens(ptr(tok), ptr(pos), ptr(out), B, T, tokens_per_image, D, _stream()),
+          "vitk_prefix_tokens")
+    launch_count += 1
