@@ -1,0 +1,88 @@
+"""Batch-sharded data parallelism for the fused ViT path: one process per GPU, bucketed NCCL gradient all-reduce
+overlapped with backward (the reference itself is single-GPU, utils_network.py:406-452).
+
+Buckets are the flat fp32 gradient buffers that functional.BlockFn.backward fills (one per transformer block, in
+reverse layer order as backward runs) plus one trailing bucket for the remaining parameters (patch_embed, cls/pos,
+final norm, head). Each block bucket is all-reduced (average) on a dedicated communication stream as soon as the block's
+backward has been enqueued, so the 12 collectives overlap the rest of backward; `finish()` joins the streams before the
+optimizer step. No DistributedDataParallel wrapper: unused parameters (the DINO fine-tune `head`)
+simply never produce a bucket.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import functional as Fn
+
+
+class GradAllReducer:
+    def __init__(self, model: torch.nn.Module, process_group=None, overlap: bool = True):
+        self.model = model
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.overlap = overlap
+        self.cuda = next(model.parameters()).is_cuda
+        self.comm_stream = torch.cuda.Stream() if self.cuda else None
+        self._pending = []   # (flat buffer, work handle)
+        self._bucketed_ptrs = set()
+        self.collectives = 0
+        if self.world > 1:
+            Fn.grad_bucket_hooks.append(self._on_bucket)
+
+    def close(self):
+        if self._on_bucket in Fn.grad_bucket_hooks:
+            Fn.grad_bucket_hooks.remove(self._on_bucket)
+
+    # called from BlockFn.backward on the compute stream once the block's flat gradient buffer is fully enqueued
+    def _on_bucket(self, buf: torch.Tensor, params, views):
+        if not self.overlap:
+            self._pending.append((buf, None, params, views))
+            return
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                work = dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.pg, async_op=True)
+            buf.record_stream(self.comm_stream)
+        else:  # gloo (CPU tests): no AVG, no streams
+            work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        self.collectives += 1
+        self._pending.append((buf, work, params, views))
+
+    def finish(self):
+        """Join the overlapped collectives, reduce whatever was not covered by a block bucket, and make sure every
+        param.grad holds the averaged gradient. Call after loss.backward(), before optimizer.step()."""
+        if self.world <= 1:
+            return
+        covered = set()
+        for buf, work, params, views in self._pending:
+            if work is None:
+                dist.all_reduce(buf, op=dist.ReduceOp.AVG if self.cuda else dist.ReduceOp.SUM, group=self.pg)
+                self.collectives += 1
+            else:
+                work.wait()
+            if not self.cuda:
+                buf.div_(self.world)
+            # .grad normally IS the bucket view (autograd steals it when .grad was None); if autograd cloned or
+            # accumulated instead, overwrite it with the reduced bucket contents.
+            for p, v in zip(params, views):
+                if p is None or v is None:
+                    continue
+                covered.add(id(p))
+                if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                    p.grad.copy_(v)
+        self._pending.clear()
+        rest = [p.grad for p in self.model.parameters() if p.grad is not None and id(p) not in covered]
+        if rest:
+            flat = torch.cat([g.reshape(-1) for g in rest])
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG if self.cuda else dist.ReduceOp.SUM, group=self.pg)
+            if not self.cuda:
+                flat.div_(self.world)
+            self.collectives += 1
+            off = 0
+            for g in rest:
+                n = g.numel()
+                g.copy_(flat[off:off + n].view_as(g))
+                off += n

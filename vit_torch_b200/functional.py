@@ -101,6 +101,7 @@ class BlockFn(torch.autograd.Function):
                                   projw, n2w, fc1w, fc2w, g1, g2, rowscale, wqkv, wproj, wfc1, wfc2)
             ctx.dims = (B, N, D, H, d, scale)
             ctx.has = (qkvb is not None, projb is not None, fc1b is not None, fc2b is not None)
+            ctx.param_refs = [n1w, n1b, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b, g1, g2]
         return x2.view(B, N, D)
 
     @staticmethod
@@ -166,13 +167,17 @@ class BlockFn(torch.autograd.Function):
         dx0, dx0b = ops.layernorm_bwd(dh1, x0, n1w, mean1, rstd1, dres=dx1, dweight=dn1w, dbias=dn1b, want_bf16=True)
         dx = dx0.view(B, N, D)
         dx._vitk_bf16 = dx0b
-        for hook in grad_bucket_hooks:
-            hook(buf)
+        if grad_bucket_hooks:
+            # hand the hooks their own alias views so the returned ones stay uniquely referenced (autograd then adopts
+            # them as .grad without cloning)
+            alias = [None if v is None else v.view(v.shape) for v in gv]
+            for hook in grad_bucket_hooks:
+                hook(buf, ctx.param_refs, alias)
         return (dx, None, None, None, None, dn1w, dn1b, dqkvw, dqkvb, dprojw, dprojb, dn2w, dn2b, dfc1w, dfc1b,
                 dfc2w, dfc2b, dg1, dg2)
 
 
-# callbacks(flat_grad_buffer) fired when one block's parameter gradients are complete (used by dist.py)
+# callbacks(flat_grad_buffer, params, grad_views) fired when one block's parameter gradients are complete (used by dist.py)
 grad_bucket_hooks: list = []
 
 

@@ -21,6 +21,23 @@ EPI_STORE_F32 = 5
 launch_count = 0
 
 
+# optional per-launch CUDA-event timing of the GEMM kernel (bench.py roofline pass)
+_gemm_events = None
+
+
+def gemm_timing_begin():
+    global _gemm_events
+    _gemm_events = []
+
+
+def gemm_timing_end():
+    """Returns (total GEMM kernel milliseconds, number of GEMM launches) since gemm_timing_begin()."""
+    global _gemm_events
+    ev, _gemm_events = _gemm_events, None
+    torch.cuda.synchronize()
+    return sum(s.elapsed_time(e) for s, e in ev), len(ev)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -56,6 +73,9 @@ def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, epilogue=EPI_S
         N = b.shape[1] if b_mn else b.shape[0]
     lib = _lib.load()
     tok_n, tok_N, tok_T = tok if tok is not None else (0, 0, 0)
+    if _gemm_events is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = lib.vitk_gemm_bf16_ex(
         ptr(a), _ld(a), int(a_mn), ptr(b), _ld(b), int(b_mn), M, N, K, epilogue,
         ptr(bias), ptr(gamma), ptr(resid), _ld(resid) if resid is not None else 0,
@@ -63,6 +83,10 @@ def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, epilogue=EPI_S
         ptr(aux), _ld(aux) if aux is not None else 0, splits, ptr(rowscale), rows_per_sample, tok_n, tok_N, tok_T,
         _stream())
     check(rc, "vitk_gemm_bf16_ex")
+    if _gemm_events is not None:
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        _gemm_events.append((ev0, ev1))
     launch_count += 1
     return out
 
