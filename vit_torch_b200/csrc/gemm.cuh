@@ -56,90 +56,81 @@ template <int BN> struct GemmCfg {
     static constexpr int STAGES = (BN == 256) ? 4 : 6;
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
+    static constexpr int VEC_BYTES = 2 * 2 * BN * 4;  // double-buffered bias[BN] and gamma[BN] for the epilogue
+    static constexpr int STG_BYTES = GEMM_EPI_WARPS * 32 * 16 * 4;  // per-warp [32 rows x 16 fp32] transpose buffer
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + VEC_BYTES + STG_BYTES + 1024;  // +1 KB: align
+};
+
+// ----------------------------------------------------------------------------------------------------------------
+// Epilogue math on 4 consecutive columns of one row, executed in the COALESCED domain: after the accumulator chunk has
+// been transposed through shared memory, the 8 lanes lane/8.. of a warp own 4 columns each of the same row, so that
+// every global load/store instruction touches whole 32-byte sectors of a few rows.
+// ----------------------------------------------------------------------------------------------------------------
+struct EpiOperand {  // operands that do not depend on the accumulator; fetched before the accumulator is waited on
+    float4 r;        // residual (EPI_RESID_F32) / positional embedding (EPI_TOKENS_F32)
+    uint2 aux;       // 4 bf16 pre-activations (EPI_DGELU)
 };
 
 template <int EPI>
-__device__ __forceinline__ void gemm_epilogue_8cols(const GemmArgs& g, const float* acc, long long row, int col) {
-    // acc: 8 fp32 accumulators for columns col..col+7 of one row (row < M, col + 8 <= N guaranteed by caller)
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = acc[i];
-    if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32 ||
-                  EPI == EPI_TOKENS_F32) {
-        if (g.bias != nullptr) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + col));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + col + 4));
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-        }
-    }
-    if constexpr (EPI == EPI_STORE_BF16) {
-        uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-        st_v4(reinterpret_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col, o);
-    } else if constexpr (EPI == EPI_BIAS_GELU) {
-        if (g.out != nullptr) {  // pre-activation is only needed for backward
-            uint4 o =
-                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            st_v4(reinterpret_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col, o);
-        }
-        float a[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = gelu_f(v[i]);
-        uint4 o2 = make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
-        st_v4(reinterpret_cast<__nv_bfloat16*>(g.out2) + row * g.ldo2 + col, o2);
-    } else if constexpr (EPI == EPI_RESID_F32) {
-        if (g.out2 != nullptr) {
-            uint4 o2 =
-                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            st_v4(reinterpret_cast<__nv_bfloat16*>(g.out2) + row * g.ldo2 + col, o2);
-        }
-        if (g.gamma != nullptr) {
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(g.gamma + col));
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(g.gamma + col + 4));
-            v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
-            v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
-        }
-        if (g.rowscale != nullptr) {
-            const float rs = __ldg(g.rowscale + row / g.rows_per_sample);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] *= rs;
-        }
-        float* o = reinterpret_cast<float*>(g.out) + row * g.ldo + col;
-        if (g.resid != nullptr) {
-            const float* r = g.resid + row * g.ldr + col;
-            const float4 r0 = *reinterpret_cast<const float4*>(r);
-            const float4 r1 = *reinterpret_cast<const float4*>(r + 4);
-            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-            v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-        }
-        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+__device__ __forceinline__ void epi_fetch(const GemmArgs& g, EpiOperand& op, long long row, int col) {
+    if constexpr (EPI == EPI_RESID_F32) {
+        if (g.resid != nullptr) op.r = *reinterpret_cast<const float4*>(g.resid + row * g.ldr + col);
     } else if constexpr (EPI == EPI_DGELU) {
-        const uint4 a = *reinterpret_cast<const uint4*>(g.aux + row * g.ldaux + col);
-        v[0] *= gelu_grad_f(bf16_lo(a.x)); v[1] *= gelu_grad_f(bf16_hi(a.x));
-        v[2] *= gelu_grad_f(bf16_lo(a.y)); v[3] *= gelu_grad_f(bf16_hi(a.y));
-        v[4] *= gelu_grad_f(bf16_lo(a.z)); v[5] *= gelu_grad_f(bf16_hi(a.z));
-        v[6] *= gelu_grad_f(bf16_lo(a.w)); v[7] *= gelu_grad_f(bf16_hi(a.w));
-        uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-        st_v4(reinterpret_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col, o);
-    } else if constexpr (EPI == EPI_ATOMIC_F32) {
-        float* o = reinterpret_cast<float*>(g.out) + row * g.ldo + col;
-        red_add_v4_f32(o, v[0], v[1], v[2], v[3]);
-        red_add_v4_f32(o + 4, v[4], v[5], v[6], v[7]);
-    } else if constexpr (EPI == EPI_STORE_F32) {
-        float* o = reinterpret_cast<float*>(g.out) + row * g.ldo + col;
-        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        op.aux = *reinterpret_cast<const uint2*>(g.aux + row * g.ldaux + col);
     } else if constexpr (EPI == EPI_TOKENS_F32) {
         const long long bimg = row / g.tok_n;
         const int p = static_cast<int>(row - bimg * g.tok_n);
-        const float* pos = g.resid + (long long)(g.tok_T + p) * g.ldr + col;
-        const float4 r0 = __ldg(reinterpret_cast<const float4*>(pos));
-        const float4 r1 = __ldg(reinterpret_cast<const float4*>(pos + 4));
-        float* o = reinterpret_cast<float*>(g.out) + (bimg * g.tok_N + g.tok_T + p) * g.ldo + col;
-        *reinterpret_cast<float4*>(o) = make_float4(v[0] + r0.x, v[1] + r0.y, v[2] + r0.z, v[3] + r0.w);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4] + r1.x, v[5] + r1.y, v[6] + r1.z, v[7] + r1.w);
+        op.r = __ldg(reinterpret_cast<const float4*>(g.resid + (long long)(g.tok_T + p) * g.ldr + col));
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_apply(const GemmArgs& g, float4 v, long long row, int col, const float* sbias,
+                                          const float* sgamma, const EpiOperand& op) {
+    if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32 ||
+                  EPI == EPI_TOKENS_F32) {
+        if (g.bias != nullptr) {
+            const float4 b = *reinterpret_cast<const float4*>(sbias);
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+    }
+    if constexpr (EPI == EPI_STORE_BF16) {
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col) =
+            make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    } else if constexpr (EPI == EPI_BIAS_GELU) {
+        if (g.out != nullptr)  // pre-activation is only needed for backward
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col) =
+                make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out2) + row * g.ldo2 + col) =
+            make_uint2(pack_bf16(gelu_f(v.x), gelu_f(v.y)), pack_bf16(gelu_f(v.z), gelu_f(v.w)));
+    } else if constexpr (EPI == EPI_RESID_F32) {
+        if (g.out2 != nullptr)
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out2) + row * g.ldo2 + col) =
+                make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        if (g.gamma != nullptr) {
+            const float4 gm = *reinterpret_cast<const float4*>(sgamma);
+            v.x *= gm.x; v.y *= gm.y; v.z *= gm.z; v.w *= gm.w;
+        }
+        if (g.rowscale != nullptr) {
+            const float rs = __ldg(g.rowscale + row / g.rows_per_sample);
+            v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
+        }
+        if (g.resid != nullptr) { v.x += op.r.x; v.y += op.r.y; v.z += op.r.z; v.w += op.r.w; }
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + row * g.ldo + col) = v;
+    } else if constexpr (EPI == EPI_DGELU) {
+        v.x *= gelu_grad_f(bf16_lo(op.aux.x)); v.y *= gelu_grad_f(bf16_hi(op.aux.x));
+        v.z *= gelu_grad_f(bf16_lo(op.aux.y)); v.w *= gelu_grad_f(bf16_hi(op.aux.y));
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col) =
+            make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    } else if constexpr (EPI == EPI_ATOMIC_F32) {
+        red_add_v4_f32(reinterpret_cast<float*>(g.out) + row * g.ldo + col, v.x, v.y, v.z, v.w);
+    } else if constexpr (EPI == EPI_STORE_F32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + row * g.ldo + col) = v;
+    } else if constexpr (EPI == EPI_TOKENS_F32) {
+        const long long bimg = row / g.tok_n;
+        const int p = static_cast<int>(row - bimg * g.tok_n);
+        v.x += op.r.x; v.y += op.r.y; v.z += op.r.z; v.w += op.r.w;
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + (bimg * g.tok_N + g.tok_T + p) * g.ldo + col) = v;
     }
 }
 
@@ -160,6 +151,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
     uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]   epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* svec = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);  // [2][bias BN | gamma BN]
+    float* sstage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + Cfg::VEC_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -268,34 +261,77 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         constexpr int COLS_PER_WARP = BN / 2;
         int as = 0;
         uint32_t aphase = 0;
+        const int et = threadIdx.x - GEMM_EPI_WARP0 * 32;  // 0..255 within the epilogue warps
+        constexpr bool kUsesVec = (EPI == EPI_STORE_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32 ||
+                                   EPI == EPI_STORE_F32 || EPI == EPI_TOKENS_F32);
         for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
             const int n_tile = u % g.num_n_tiles;
             const int rest = u / g.num_n_tiles;
             const int m_tile = rest / g.splits;
-            const long long row = (long long)m_tile * GEMM_BM + quarter * 32 + lane;
+            float* sb = svec + as * 2 * BN;  // buffer index follows the accumulator stage (alternates per tile)
+            float* sg = sb + BN;
+            if constexpr (kUsesVec) {
+                // stage bias / gamma of this N tile in shared memory while the mainloop is still running
+                if (g.bias != nullptr || g.gamma != nullptr) {
+                    if (et < BN) {
+                        const int cidx = n_tile * BN + et;
+                        if (g.bias != nullptr) sb[et] = (cidx < g.N) ? __ldg(g.bias + cidx) : 0.f;
+                        if (g.gamma != nullptr) sg[et] = (cidx < g.N) ? __ldg(g.gamma + cidx) : 0.f;
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
+            }
+            // coalesced-domain coordinates of this lane: 8 rows per pass, 4 lanes x 4 columns per row
+            const long long row_base = (long long)m_tile * GEMM_BM + quarter * 32;
             const int n0 = n_tile * BN + half * COLS_PER_WARP;
+            const int sub_row = lane >> 2, sub_col = (lane & 3) * 4;
+            float* stg = sstage + ew * (32 * 16);
+            constexpr int NCHUNK = COLS_PER_WARP / 16;
+            EpiOperand nxt[4];
+            auto fetch_chunk = [&](int c) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const long long rr = row_base + it * 8 + sub_row;
+                    const int col = n0 + c * 16 + sub_col;
+                    if (rr < g.M && col + 4 <= g.N) epi_fetch<EPI>(g, nxt[it], rr, col);
+                }
+            };
+            fetch_chunk(0);  // operands that do not depend on the accumulator: in flight while we wait for the MMAs
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN + half * COLS_PER_WARP;
 #pragma unroll 1
-            for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(taddr + c * 32, r);
+            for (int c = 0; c < NCHUNK; ++c) {
+                uint32_t r[16];
+                tmem_ld_32x32b_x16(taddr + c * 16, r);
                 tmem_ld_wait();
-                if (c == COLS_PER_WARP / 32 - 1) {
+                if (c == NCHUNK - 1) {
                     // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty_bar[as]);
                 }
-                if (row < g.M) {
+                // transpose through shared memory: TMEM domain (lane == row) -> coalesced domain. 16-byte units are
+                // XOR-swizzled with (row >> 1) so that both the row-wise writes and the 8-row reads are conflict free.
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int col = n0 + c * 32 + q * 8;
-                        if (col + 8 <= g.N)
-                            gemm_epilogue_8cols<EPI>(g, reinterpret_cast<const float*>(r) + q * 8, row, col);
-                    }
+                for (int u = 0; u < 4; ++u)
+                    *reinterpret_cast<uint4*>(stg + lane * 16 + ((u ^ (lane >> 1)) & 3) * 4) =
+                        make_uint4(r[u * 4 + 0], r[u * 4 + 1], r[u * 4 + 2], r[u * 4 + 3]);
+                __syncwarp();
+                EpiOperand cur[4];
+#pragma unroll
+                for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
+                if (c + 1 < NCHUNK) fetch_chunk(c + 1);
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int lr = it * 8 + sub_row;
+                    const float4 v = *reinterpret_cast<const float4*>(stg + lr * 16 + (((lane & 3) ^ (lr >> 1)) & 3) * 4);
+                    const long long rr = row_base + lr;
+                    const int col = n0 + c * 16 + sub_col;
+                    const int lc = half * COLS_PER_WARP + c * 16 + sub_col;  // column within the N tile
+                    if (rr < g.M && col + 4 <= g.N) epi_apply<EPI>(g, v, rr, col, sb + lc, sg + lc, cur[it]);
                 }
+                __syncwarp();
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }

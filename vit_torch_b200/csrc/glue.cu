@@ -71,52 +71,72 @@ ln_fwd_kernel(const float* __restrict__ x, long long x_stride, const float* __re
 //   dx = dres + rstd * (dy*w - mean_D(dy*w) - xhat * mean_D(dy*w*xhat));  dw += sum_rows dy*xhat;  db += sum_rows dy
 // ------------------------------------------------------------------------------------------------
 template <int MAXC, bool DY_F32>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LN_WARPS * 32, 2)
 ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long long x_stride,
               const float* __restrict__ w, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               const float* __restrict__ dres, float* __restrict__ dx, long long dx_stride,
               __nv_bfloat16* __restrict__ dx_bf16, const float* __restrict__ colscale, float* __restrict__ dweight,
               float* __restrict__ dbias, long long rows, int D) {
-    __shared__ float red[LN_WARPS * MAXC * 128];
+    // smem: w[Dp] | per-warp partials [LN_WARPS][2][Dp] (dweight, dbias). Keeping the partial sums and the weight in
+    // shared memory instead of registers leaves room for two 8-warp blocks per SM with all loads of a row in flight.
+    constexpr int Dp = MAXC * 128;
+    extern __shared__ __align__(16) float ln_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4 wv[MAXC], dwa[MAXC], dba[MAXC];
+    float* sw = ln_smem;
+    float* pw = ln_smem + Dp + warp * 2 * Dp;
+    float* pb = pw + Dp;
+    for (int c = threadIdx.x; c < Dp; c += LN_WARPS * 32) sw[c] = (c < D) ? w[c] : 0.f;
 #pragma unroll
     for (int i = 0; i < MAXC; ++i) {
         const int c = (i * 32 + lane) * 4;
-        wv[i] = (c < D) ? __ldg(reinterpret_cast<const float4*>(w + c)) : make_float4(0, 0, 0, 0);
-        dwa[i] = make_float4(0, 0, 0, 0);
-        dba[i] = make_float4(0, 0, 0, 0);
+        *reinterpret_cast<float4*>(pw + c) = make_float4(0, 0, 0, 0);
+        *reinterpret_cast<float4*>(pb + c) = make_float4(0, 0, 0, 0);
     }
+    __syncthreads();
     const float inv_d = 1.0f / static_cast<float>(D);
     for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
-        const float mean = mean_in[row], rstd = rstd_in[row];
         const float* xr = x + row * x_stride;
-        float4 xh[MAXC], g[MAXC];
+        float4 xv[MAXC], dv[MAXC], rv[MAXC];
+        // issue every global load of the row before the first use
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < D) {
+                xv[i] = *reinterpret_cast<const float4*>(xr + c);
+                if constexpr (DY_F32) {
+                    dv[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + row * D + c);
+                } else {
+                    const uint2 t =
+                        *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy_) + row * D + c);
+                    dv[i] = make_float4(bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y));
+                }
+                rv[i] = (dres != nullptr) ? *reinterpret_cast<const float4*>(dres + row * dx_stride + c)
+                                          : make_float4(0, 0, 0, 0);
+            } else {
+                xv[i] = make_float4(0, 0, 0, 0);
+                dv[i] = make_float4(0, 0, 0, 0);
+                rv[i] = make_float4(0, 0, 0, 0);
+            }
+        }
+        const float mean = mean_in[row], rstd = rstd_in[row];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < MAXC; ++i) {
             const int c = (i * 32 + lane) * 4;
             if (c < D) {
-                const float4 xv = *reinterpret_cast<const float4*>(xr + c);
-                float d0, d1, d2, d3;
-                if constexpr (DY_F32) {
-                    const float4 dv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + row * D + c);
-                    d0 = dv.x; d1 = dv.y; d2 = dv.z; d3 = dv.w;
-                } else {
-                    const uint2 dv =
-                        *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy_) + row * D + c);
-                    d0 = bf16_lo(dv.x); d1 = bf16_hi(dv.x); d2 = bf16_lo(dv.y); d3 = bf16_hi(dv.y);
-                }
-                xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd,
-                                    (xv.w - mean) * rstd);
-                g[i] = make_float4(d0 * wv[i].x, d1 * wv[i].y, d2 * wv[i].z, d3 * wv[i].w);
-                dwa[i].x += d0 * xh[i].x; dwa[i].y += d1 * xh[i].y; dwa[i].z += d2 * xh[i].z; dwa[i].w += d3 * xh[i].w;
-                dba[i].x += d0; dba[i].y += d1; dba[i].z += d2; dba[i].w += d3;
-                s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
-                s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
-            } else {
-                xh[i] = make_float4(0, 0, 0, 0);
-                g[i] = make_float4(0, 0, 0, 0);
+                const float4 wv = *reinterpret_cast<const float4*>(sw + c);
+                // xv <- xhat ; dv stays dy ; g = dy * w
+                xv[i] = make_float4((xv[i].x - mean) * rstd, (xv[i].y - mean) * rstd, (xv[i].z - mean) * rstd,
+                                    (xv[i].w - mean) * rstd);
+                float4 aw = *reinterpret_cast<float4*>(pw + c);
+                float4 ab = *reinterpret_cast<float4*>(pb + c);
+                aw.x += dv[i].x * xv[i].x; aw.y += dv[i].y * xv[i].y; aw.z += dv[i].z * xv[i].z; aw.w += dv[i].w * xv[i].w;
+                ab.x += dv[i].x; ab.y += dv[i].y; ab.z += dv[i].z; ab.w += dv[i].w;
+                *reinterpret_cast<float4*>(pw + c) = aw;
+                *reinterpret_cast<float4*>(pb + c) = ab;
+                dv[i] = make_float4(dv[i].x * wv.x, dv[i].y * wv.y, dv[i].z * wv.z, dv[i].w * wv.w);
+                s1 += (dv[i].x + dv[i].y) + (dv[i].z + dv[i].w);
+                s2 += (dv[i].x * xv[i].x + dv[i].y * xv[i].y) + (dv[i].z * xv[i].z + dv[i].w * xv[i].w);
             }
         }
         const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
@@ -124,12 +144,10 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long lo
         for (int i = 0; i < MAXC; ++i) {
             const int c = (i * 32 + lane) * 4;
             if (c < D) {
-                float4 o = make_float4(rstd * (g[i].x - c1 - xh[i].x * c2), rstd * (g[i].y - c1 - xh[i].y * c2),
-                                       rstd * (g[i].z - c1 - xh[i].z * c2), rstd * (g[i].w - c1 - xh[i].w * c2));
-                if (dres != nullptr) {
-                    const float4 r = *reinterpret_cast<const float4*>(dres + row * dx_stride + c);
-                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                }
+                float4 o = make_float4(rstd * (dv[i].x - c1 - xv[i].x * c2) + rv[i].x,
+                                       rstd * (dv[i].y - c1 - xv[i].y * c2) + rv[i].y,
+                                       rstd * (dv[i].z - c1 - xv[i].z * c2) + rv[i].z,
+                                       rstd * (dv[i].w - c1 - xv[i].w * c2) + rv[i].w);
                 if (dx != nullptr) *reinterpret_cast<float4*>(dx + row * dx_stride + c) = o;
                 if (dx_bf16 != nullptr) {
                     if (colscale != nullptr) {
@@ -141,25 +159,18 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long lo
             }
         }
     }
-    // block reduction of the per-warp dweight / dbias partials, then one atomic per column per block
-    const int Dp = MAXC * 128;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        float* dst = pass == 0 ? dweight : dbias;
-        if (dst == nullptr) continue;
-        __syncthreads();
+    // block reduction of the per-warp partials, then one atomic per column per block
+    __syncthreads();
+    const float* part = ln_smem + Dp;
+    for (int c = threadIdx.x; c < D; c += LN_WARPS * 32) {
+        float a = 0.f, bsum = 0.f;
 #pragma unroll
-        for (int i = 0; i < MAXC; ++i) {
-            const int c = (i * 32 + lane) * 4;
-            *reinterpret_cast<float4*>(&red[warp * Dp + c]) = pass == 0 ? dwa[i] : dba[i];
+        for (int k = 0; k < LN_WARPS; ++k) {
+            a += part[k * 2 * Dp + c];
+            bsum += part[k * 2 * Dp + Dp + c];
         }
-        __syncthreads();
-        for (int c = threadIdx.x; c < D; c += LN_WARPS * 32) {
-            float s = 0.f;
-#pragma unroll
-            for (int k = 0; k < LN_WARPS; ++k) s += red[k * Dp + c];
-            atomicAdd(dst + c, s);
-        }
+        if (dweight != nullptr) atomicAdd(dweight + c, a);
+        if (dbias != nullptr) atomicAdd(dbias + c, bsum);
     }
 }
 
@@ -380,24 +391,34 @@ static int ln_bwd_impl(const void* dy, int dy_is_f32, const float* x, long long 
     if (!dy || !x || !weight || !mean || !rstd) return VITK_ERR_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     long long need = (rows + LN_WARPS - 1) / LN_WARPS;
-    const long long cap = (long long)sm_count() * 4;
+    const long long cap = (long long)sm_count() * 2;
     const int grid = (int)(need < cap ? need : cap);
     auto dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
     const int chunks = (D + 127) / 128;
-#define VITK_LN_BWD(C)                                                                                                \
-    do {                                                                                                              \
-        if (dy_is_f32)                                                                                                \
-            ln_bwd_kernel<C, true><<<grid, LN_WARPS * 32, 0, st>>>(dy, x, x_stride, weight, mean, rstd, dres, dx,     \
-                                                                   dx_stride, dxb, colscale, dweight, dbias, rows, D); \
-        else                                                                                                          \
-            ln_bwd_kernel<C, false><<<grid, LN_WARPS * 32, 0, st>>>(dy, x, x_stride, weight, mean, rstd, dres, dx,    \
-                                                                    dx_stride, dxb, colscale, dweight, dbias, rows, D); \
+#define VITK_LN_BWD_ONE(C, F)                                                                                        \
+    do {                                                                                                             \
+        constexpr int smem = (1 + 2 * LN_WARPS) * (C) * 128 * 4;                                                     \
+        static bool attr = false;                                                                                    \
+        if (!attr) {                                                                                                 \
+            if (cudaFuncSetAttribute(ln_bwd_kernel<C, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=      \
+                cudaSuccess)                                                                                         \
+                return VITK_ERR_CUDA;                                                                                \
+            attr = true;                                                                                             \
+        }                                                                                                            \
+        ln_bwd_kernel<C, F><<<grid, LN_WARPS * 32, smem, st>>>(dy, x, x_stride, weight, mean, rstd, dres, dx,        \
+                                                               dx_stride, dxb, colscale, dweight, dbias, rows, D);   \
+    } while (0)
+#define VITK_LN_BWD(C)                      \
+    do {                                    \
+        if (dy_is_f32) VITK_LN_BWD_ONE(C, true); \
+        else VITK_LN_BWD_ONE(C, false);     \
     } while (0)
     if (chunks <= 2) VITK_LN_BWD(2);
     else if (chunks <= 3) VITK_LN_BWD(3);
     else if (chunks <= 6) VITK_LN_BWD(6);
     else VITK_LN_BWD(8);
 #undef VITK_LN_BWD
+#undef VITK_LN_BWD_ONE
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
 }
 
