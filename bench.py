@@ -76,15 +76,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=0.0, t1=float("inf")):
+        """Summarise the samples taken in the wall-clock window [t0, t1] (the timed region)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        window = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        for r in window:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -236,15 +238,16 @@ def main():
         loss = trainer.step(xb, yb)
         return loss.item()                                # device -> host read of the step result
 
-    for _ in range(args.warmup):
-        step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()          # nvidia-smi needs ~1 s to come up: start it before the warm-up
+    for _ in range(args.warmup):
+        step_resident()
     l0 = ops.launch_count
+    t_begin = time.time()
     ms, loss = timed(step_resident, args.steps)
+    t_end = time.time()
     launches = (ops.launch_count - l0) + trainer.extra_launches_per_step * args.steps
-    clocks = sampler.stop() if rank == 0 else None
     value = world * bs * args.steps / (ms * 1e-3)
 
     e2e = None
@@ -273,6 +276,7 @@ def main():
                 "traffic": None, "launches": gemm_launches, "avg_launch_us": gemm_ms * 1e3 / max(gemm_launches, 1),
                 "share_of_step": gemm_ms / (ms if ms > 0 else 1.0)}
 
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args)
