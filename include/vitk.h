@@ -65,6 +65,17 @@ int vitk_gemm_bf16_ex(const void* A, long long lda, int a_mn_major, const void* 
                       int tok_T, void* stream);
 
 /*
+ * Batched GEMM: nbatch_h * nbatch_b independent problems D_b[M,N] = A_b[M,K] * B_b[N,K]^T addressed by element strides
+ * per (inner, outer) batch index -- attention-style batches over (head, image) reading q/k/v in place from the qkv
+ * Linear output. Epilogues VITK_EPI_STORE_BF16 / VITK_EPI_STORE_F32 only. Used by the CaiT talking-heads attention
+ * (models/cait.py:116-125): S = q k^T, O = P' v, and their backward products. All strides % 8 == 0.
+ */
+int vitk_gemm_bf16_batched(const void* A, long long lda, long long sa_h, long long sa_b, int a_mn_major, const void* B,
+                           long long ldb, long long sb_h, long long sb_b, int b_mn_major, int M, int N, int K,
+                           int nbatch_h, int nbatch_b, int epilogue, void* out, long long ldo, long long so_h,
+                           long long so_b, void* stream);
+
+/*
  * LayerNorm forward over the last dim (nn.LayerNorm(D, eps=1e-6): models/cait.py:64,68,203,259; models/deit.py:98).
  *   x fp32 [rows, D] -> y bf16 [rows, D]; saves mean/rstd fp32 [rows]. D % 4 == 0, D <= 1024.
  */

@@ -125,7 +125,45 @@ def test_gemm_strided_views():
 def test_gemm_bad_args_fail_loudly():
     from vit_torch_b200 import ops, _lib
     a = torch.zeros((16, 16), dtype=torch.bfloat16, device="cuda")
-    b = torch.zeros((12, 16), dtype=torch.bfloat16, device="cuda")
-    out = torch.zeros((16, 12), device="cuda")
-    with pytest.raises(_lib.VitkError):
-        ops.gemm(a, b, epilogue=ops.EPI_STORE_F32, out=out)   # N % 8 != 0
+    b = torch.zeros((10, 16), dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(_lib.VitkError):   # N = 10 needs 12 output columns, the output pitch has only 10
+        ops.gemm(a, b, epilogue=ops.EPI_STORE_F32, out=torch.zeros((16, 10), device="cuda"))
+    with pytest.raises(_lib.VitkError):   # operand pitch must be a multiple of 8 elements (16-byte TMA stride)
+        ops.gemm(torch.zeros((16, 12), dtype=torch.bfloat16, device="cuda"),
+                 torch.zeros((16, 12), dtype=torch.bfloat16, device="cuda"), epilogue=ops.EPI_STORE_F32,
+                 out=torch.zeros((16, 16), device="cuda"))
+
+
+@pytest.mark.parametrize("B,N,H,d", [(2, 196, 8, 48), (3, 197, 2, 64), (1, 577, 4, 48)])
+def test_gemm_batched_attention_products(B, N, H, d):
+    """Batched mode over (head, image), operands read in place from the token-major qkv buffer: the three products the
+    CaiT talking-heads attention needs (scores, P.V, P^T.dO)."""
+    from vit_torch_b200 import ops
+    D = H * d
+    Np = (N + 7) // 8 * 8
+    qkv = _mk((B * N, 3 * D), 21).to(torch.bfloat16)
+    q, k, v = qkv.float().reshape(B, N, 3, H, d).permute(2, 0, 3, 1, 4)
+    # S[b,h,i,j] = q.k  (fp32 out, row pitch Np)
+    S = torch.zeros((B, H, N, Np), device="cuda")
+    ops.gemm_batched(qkv, 3 * D, d, N * 3 * D, False, qkv, 3 * D, d, N * 3 * D, False, N, N, d, H, B, S, Np, N * Np,
+                     H * N * Np, a_off=0, b_off=D, out_f32=True)
+    ref = q @ k.transpose(-2, -1)
+    assert nerr(S[..., :N], ref) <= 1e-3
+    assert S[..., N:].abs().max().item() == 0.0 if Np > N else True
+    # O[b,i,h,:] = P[b,h,i,:] . v[b,:,h,:]
+    P = torch.zeros((B, H, N, Np), device="cuda", dtype=torch.bfloat16)
+    P[..., :N] = torch.softmax(ref * d ** -0.5, -1).to(torch.bfloat16)
+    O = torch.zeros((B * N, D), device="cuda", dtype=torch.bfloat16)
+    ops.gemm_batched(P, Np, N * Np, H * N * Np, False, qkv, 3 * D, d, N * 3 * D, True, N, d, N, H, B, O, D, d, N * D,
+                     b_off=2 * D)
+    ref_o = (P[..., :N].float() @ v).transpose(1, 2).reshape(B * N, D)
+    assert nerr(O, ref_o) <= 1e-2
+    # dV[b,j,h,:] = sum_i P[b,h,i,j] dO[b,i,h,:]   (both operands MN-major), written into the V third of a dqkv buffer
+    dO = _mk((B * N, D), 22).to(torch.bfloat16)
+    dqkv = torch.zeros((B * N, 3 * D), device="cuda", dtype=torch.bfloat16)
+    ops.gemm_batched(P, Np, N * Np, H * N * Np, True, dO, D, d, N * D, True, N, d, N, H, B, dqkv, 3 * D, d, N * 3 * D,
+                     out_off=2 * D)
+    ref_dv = (P[..., :N].float().transpose(-2, -1) @ dO.float().reshape(B, N, H, d).permute(0, 2, 1, 3))
+    got = dqkv.float().reshape(B, N, 3, H, d)[:, :, 2].permute(0, 2, 1, 3)
+    assert nerr(got, ref_dv) <= 1e-2
+    assert dqkv[:, :2 * D].abs().max().item() == 0.0

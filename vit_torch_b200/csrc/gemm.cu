@@ -35,7 +35,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
             return VITK_ERR_CUDA;
         attr_set = true;
     }
-    const int units = g.num_m_tiles * g.num_n_tiles * g.splits;
+    const int units = g.num_m_tiles * g.num_n_tiles * g.splits * g.nbatch_h * g.nbatch_b;
     const int grid = units < sm_count() ? units : sm_count();
     kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
@@ -59,6 +59,7 @@ static int dispatch_gemm(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, co
     // wgrad: dY^T and X^T, both MN-major, split-K accumulate
     VITK_CASE(1, 1, EPI_ATOMIC_F32)
     VITK_CASE(1, 1, EPI_STORE_F32)
+    VITK_CASE(1, 1, EPI_STORE_BF16)
     VITK_CASE(1, 0, EPI_STORE_F32)
 #undef VITK_CASE
     return VITK_ERR_UNSUPPORTED;
@@ -68,25 +69,38 @@ static int dispatch_gemm(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, co
 
 using namespace vitk;
 
+struct GemmBatch {
+    int nh = 1, nb = 1;
+    long long sa_h = 0, sa_b = 0, sb_h = 0, sb_b = 0, so_h = 0, so_b = 0;  // element strides
+};
+
 static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major, int M,
                      int N, int K, int epilogue, const float* bias, const float* gamma, const float* resid,
                      long long ldr, void* out, long long ldo, void* out2, long long ldo2, const void* aux,
                      long long ldaux, int splits, const float* rowscale, int rows_per_sample, int tok_n, int tok_N,
-                     int tok_T, void* stream) {
+                     int tok_T, void* stream, const GemmBatch& bt = GemmBatch()) {
     if (M <= 0 || N <= 0 || K <= 0) return VITK_ERR_ARG;
-    if ((N % 8) != 0 || (lda % 8) != 0 || (ldb % 8) != 0) return VITK_ERR_ARG;
+    if ((lda % 8) != 0 || (ldb % 8) != 0) return VITK_ERR_ARG;
+    // The epilogue works on 4-column groups. N that is not a multiple of 4 is allowed for the plain store epilogues when
+    // the output pitch has room for the rounded-up width: the extra columns come out as zeros (TMA zero-fills B rows >= N).
+    const int Nepi = (N + 3) & ~3;
+    if (Nepi != N && (ldo < Nepi || bias || gamma || resid || aux || out2 ||
+                      !(epilogue == EPI_STORE_BF16 || epilogue == EPI_STORE_F32)))
+        return VITK_ERR_ARG;
+    if ((epilogue == EPI_STORE_BF16 || epilogue == EPI_BIAS_GELU || epilogue == EPI_DGELU) && (ldo % 4) != 0)
+        return VITK_ERR_ARG;
     if (A == nullptr || B == nullptr) return VITK_ERR_ARG;
     if (out == nullptr && !(epilogue == EPI_BIAS_GELU && out2 != nullptr)) return VITK_ERR_ARG;
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(out)) & 15)
         return VITK_ERR_ARG;
     if (rowscale != nullptr && rows_per_sample <= 0) return VITK_ERR_ARG;
     if (epilogue == EPI_TOKENS_F32 && (tok_n <= 0 || tok_N < tok_n + tok_T || resid == nullptr)) return VITK_ERR_ARG;
-    const int BN = (N % 256 == 0 || N >= 1024) ? 256 : 128;
+    const int BN = (Nepi % 256 == 0 || Nepi >= 1024) ? 256 : 128;
 
     GemmArgs g;
-    g.M = M; g.N = N; g.K = K;
+    g.M = M; g.N = Nepi; g.K = K;
     g.num_m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
-    g.num_n_tiles = (N + BN - 1) / BN;
+    g.num_n_tiles = (Nepi + BN - 1) / BN;
     g.num_kblocks = (K + GEMM_BK - 1) / GEMM_BK;
     const bool accumulate = (epilogue == EPI_ATOMIC_F32);
     int s = 1;
@@ -99,17 +113,23 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
     g.aux = reinterpret_cast<const __nv_bfloat16*>(aux); g.ldaux = ldaux;
     g.rowscale = rowscale; g.rows_per_sample = rows_per_sample;
     g.tok_n = tok_n; g.tok_N = tok_N; g.tok_T = tok_T;
+    g.nbatch_h = bt.nh; g.nbatch_b = bt.nb; g.so_h = bt.so_h; g.so_b = bt.so_b;
+    if (bt.nh < 1 || bt.nb < 1) return VITK_ERR_ARG;
+    if ((bt.sa_h | bt.sa_b | bt.sb_h | bt.sb_b) % 8 != 0) return VITK_ERR_ARG;
+    if (bt.nh * bt.nb > 1 && (accumulate || !(epilogue == EPI_STORE_BF16 || epilogue == EPI_STORE_F32) || bias != nullptr))
+        return VITK_ERR_UNSUPPORTED;
     if (epilogue == EPI_BIAS_GELU && out2 == nullptr) return VITK_ERR_ARG;
     if (epilogue == EPI_DGELU && aux == nullptr) return VITK_ERR_ARG;
 
     CUtensorMap tmA, tmB;
     int rc;
     // K-major operand: global [rows, K], box {64 k, rows};  MN-major operand: global [K, rows], box {64 rows, 64 k}
-    if (!a_mn_major) rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM);
-    else             rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, GEMM_BK);
+    const uint64_t nh = bt.nh, nb = bt.nb;
+    if (!a_mn_major) rc = make_tmap_4d_bf16(&tmA, g.a_perm, A, K, M, nh, nb, lda, bt.sa_h, bt.sa_b, GEMM_BK, GEMM_BM);
+    else             rc = make_tmap_4d_bf16(&tmA, g.a_perm, A, M, K, nh, nb, lda, bt.sa_h, bt.sa_b, 64, GEMM_BK);
     if (rc) return VITK_ERR_TMAP;
-    if (!b_mn_major) rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GEMM_BK, (uint32_t)BN);
-    else             rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BK);
+    if (!b_mn_major) rc = make_tmap_4d_bf16(&tmB, g.b_perm, B, K, N, nh, nb, ldb, bt.sb_h, bt.sb_b, GEMM_BK, (uint32_t)BN);
+    else             rc = make_tmap_4d_bf16(&tmB, g.b_perm, B, N, K, nh, nb, ldb, bt.sb_h, bt.sb_b, 64, GEMM_BK);
     if (rc) return VITK_ERR_TMAP;
 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -133,4 +153,15 @@ extern "C" int vitk_gemm_bf16_ex(const void* A, long long lda, int a_mn_major, c
                                  void* stream) {
     return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, epilogue, bias, gamma, resid, ldr, out, ldo, out2,
                      ldo2, aux, ldaux, splits, rowscale, rows_per_sample, tok_n, tok_N, tok_T, stream);
+}
+
+extern "C" int vitk_gemm_bf16_batched(const void* A, long long lda, long long sa_h, long long sa_b, int a_mn_major,
+                                      const void* B, long long ldb, long long sb_h, long long sb_b, int b_mn_major,
+                                      int M, int N, int K, int nbatch_h, int nbatch_b, int epilogue, void* out,
+                                      long long ldo, long long so_h, long long so_b, void* stream) {
+    GemmBatch bt;
+    bt.nh = nbatch_h; bt.nb = nbatch_b;
+    bt.sa_h = sa_h; bt.sa_b = sa_b; bt.sb_h = sb_h; bt.sb_b = sb_b; bt.so_h = so_h; bt.so_b = so_b;
+    return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, epilogue, nullptr, nullptr, nullptr, 0, out, ldo,
+                     nullptr, 0, nullptr, 0, 1, nullptr, 0, 0, 0, 0, stream, bt);
 }

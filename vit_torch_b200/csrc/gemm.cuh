@@ -41,6 +41,11 @@ struct GemmArgs {
     const float* rowscale;  // per-sample scale (DropPath mask / keep_prob) indexed by row / rows_per_sample, or null
     int rows_per_sample;
     int tok_n, tok_N, tok_T;  // EPI_TOKENS_F32: patches per image, tokens per image, prefix tokens
+    // batched mode: nbatch_h * nbatch_b independent GEMMs (attention-style batches over (head, image)); operands are
+    // addressed through the two outer dims of the 4-D tensor maps, outputs through element strides
+    int nbatch_h, nbatch_b;
+    long long so_h, so_b;    // out strides (elements) per inner / outer batch index
+    int a_perm[3], b_perm[3];  // tensor-map dim 1+i takes logical coordinate perm[i] (0 = row, 1 = batch_h, 2 = batch_b)
 };
 
 constexpr int GEMM_BM = 128;
@@ -86,7 +91,7 @@ __device__ __forceinline__ void epi_fetch(const GemmArgs& g, EpiOperand& op, lon
 
 template <int EPI>
 __device__ __forceinline__ void epi_apply(const GemmArgs& g, float4 v, long long row, int col, const float* sbias,
-                                          const float* sgamma, const EpiOperand& op) {
+                                          const float* sgamma, const EpiOperand& op, long long ooff) {
     if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32 ||
                   EPI == EPI_TOKENS_F32) {
         if (g.bias != nullptr) {
@@ -95,7 +100,7 @@ __device__ __forceinline__ void epi_apply(const GemmArgs& g, float4 v, long long
         }
     }
     if constexpr (EPI == EPI_STORE_BF16) {
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col) =
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + ooff + row * g.ldo + col) =
             make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
     } else if constexpr (EPI == EPI_BIAS_GELU) {
         if (g.out != nullptr)  // pre-activation is only needed for backward
@@ -125,7 +130,7 @@ __device__ __forceinline__ void epi_apply(const GemmArgs& g, float4 v, long long
     } else if constexpr (EPI == EPI_ATOMIC_F32) {
         red_add_v4_f32(reinterpret_cast<float*>(g.out) + row * g.ldo + col, v.x, v.y, v.z, v.w);
     } else if constexpr (EPI == EPI_STORE_F32) {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + row * g.ldo + col) = v;
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + ooff + row * g.ldo + col) = v;
     } else if constexpr (EPI == EPI_TOKENS_F32) {
         const long long bimg = row / g.tok_n;
         const int p = static_cast<int>(row - bimg * g.tok_n);
@@ -178,7 +183,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_units = g.num_m_tiles * g.num_n_tiles * g.splits;
+    const int num_units = g.num_m_tiles * g.num_n_tiles * g.splits * g.nbatch_h * g.nbatch_b;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -189,10 +194,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int n_tile = u % g.num_n_tiles;
                 const int rest = u / g.num_n_tiles;
                 const int split = rest % g.splits;
-                const int m_tile = rest / g.splits;
+                const int mb = rest / g.splits;
+                const int m_tile = mb % g.num_m_tiles;
+                const int batch = mb / g.num_m_tiles;
+                const int bh = batch % g.nbatch_h, bb = batch / g.nbatch_h;
                 const int m0 = m_tile * GEMM_BM, n0 = n_tile * BN;
                 const int kb0 = split * g.kblocks_per_split;
                 const int kb1 = min(kb0 + g.kblocks_per_split, g.num_kblocks);
+                // operand coordinates: K-major tile = (k, row, bh, bb); MN-major tile = (row, k, bh, bb); the three
+                // outer coordinates are permuted into tensor-map dimension order
+                auto load_tile = [&](void* dst, const CUtensorMap* tm, const int* perm, int c0, int row) {
+                    const int lc[3] = {row, bh, bb};
+                    tma_load_4d(dst, tm, &full_bar[stage], c0, lc[perm[0]], lc[perm[1]], lc[perm[2]]);
+                };
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -200,18 +214,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
                     const int k0 = kb * GEMM_BK;
                     if constexpr (!A_MN) {
-                        tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);  // box {64 k, 128 m}
+                        load_tile(sa, &tmA, g.a_perm, k0, m0);  // box {64 k, 128 m}
                     } else {
 #pragma unroll
                         for (int j = 0; j < GEMM_BM / 64; ++j)  // box {64 m, 64 k} per 64-wide M chunk
-                            tma_load_2d(sa + j * (GEMM_BK * 128), &tmA, &full_bar[stage], m0 + 64 * j, k0);
+                            load_tile(sa + j * (GEMM_BK * 128), &tmA, g.a_perm, m0 + 64 * j, k0);
                     }
                     if constexpr (!B_MN) {
-                        tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);  // box {64 k, BN n}
+                        load_tile(sb, &tmB, g.b_perm, k0, n0);  // box {64 k, BN n}
                     } else {
 #pragma unroll
                         for (int j = 0; j < BN / 64; ++j)
-                            tma_load_2d(sb + j * (GEMM_BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, k0);
+                            load_tile(sb + j * (GEMM_BK * 128), &tmB, g.b_perm, n0 + 64 * j, k0);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -267,7 +281,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
             const int n_tile = u % g.num_n_tiles;
             const int rest = u / g.num_n_tiles;
-            const int m_tile = rest / g.splits;
+            const int mb = rest / g.splits;
+            const int m_tile = mb % g.num_m_tiles;
+            const int batch = mb / g.num_m_tiles;
+            const long long ooff = (long long)(batch % g.nbatch_h) * g.so_h + (long long)(batch / g.nbatch_h) * g.so_b;
             float* sb = svec + as * 2 * BN;  // buffer index follows the accumulator stage (alternates per tile)
             float* sg = sb + BN;
             if constexpr (kUsesVec) {
@@ -329,7 +346,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const long long rr = row_base + lr;
                     const int col = n0 + c * 16 + sub_col;
                     const int lc = half * COLS_PER_WARP + c * 16 + sub_col;  // column within the N tile
-                    if (rr < g.M && col + 4 <= g.N) epi_apply<EPI>(g, v, rr, col, sb + lc, sg + lc, cur[it]);
+                    if (rr < g.M && col + 4 <= g.N) epi_apply<EPI>(g, v, rr, col, sb + lc, sg + lc, cur[it], ooff);
                 }
                 __syncwarp();
             }

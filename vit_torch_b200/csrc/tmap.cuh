@@ -98,6 +98,33 @@ inline int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, 
     return make_tmap(out, ptr, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
 }
 
+// 4-D bf16 map over a batched row-major operand: logical dims (inner | rows, batch_h, batch_b) with element strides
+// (1 | pitch, stride_h, stride_b). The three outer dims are emitted in order of increasing stride (the driver wants
+// each stride to be a multiple of the previous one); perm[i] tells the kernel which logical coordinate
+// (0 = row, 1 = batch_h, 2 = batch_b) goes into map dimension 1+i.
+inline int make_tmap_4d_bf16(CUtensorMap* out, int perm[3], const void* ptr, uint64_t inner, uint64_t rows, uint64_t nh,
+                             uint64_t nb, uint64_t pitch, uint64_t stride_h, uint64_t stride_b, uint32_t box_inner,
+                             uint32_t box_rows) {
+    uint64_t ext[3] = {rows, nh, nb};
+    uint64_t str[3] = {pitch, stride_h, stride_b};
+    int order[3] = {0, 1, 2};
+    // extent-1 dims carry no addressing: give them a harmless stride and sort them last
+    uint64_t maxs = pitch * rows;
+    for (int i = 1; i < 3; ++i)
+        if (ext[i] > 1 && str[i] * ext[i] > maxs) maxs = str[i] * ext[i];
+    for (int i = 1; i < 3; ++i)
+        if (ext[i] <= 1) str[i] = maxs;
+    for (int i = 0; i < 3; ++i)
+        for (int j = i + 1; j < 3; ++j)
+            if (str[order[j]] < str[order[i]]) { int t = order[i]; order[i] = order[j]; order[j] = t; }
+    uint64_t dims[4] = {inner, ext[order[0]], ext[order[1]], ext[order[2]]};
+    uint64_t strides[3] = {str[order[0]] * 2, str[order[1]] * 2, str[order[2]] * 2};
+    uint32_t box[4] = {box_inner, order[0] == 0 ? box_rows : 1u, order[1] == 0 ? box_rows : 1u,
+                       order[2] == 0 ? box_rows : 1u};
+    for (int i = 0; i < 3; ++i) perm[i] = order[i];
+    return make_tmap(out, ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+}
+
 inline int sm_count() {
     static int n = 0;
     if (n == 0) {

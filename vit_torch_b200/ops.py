@@ -262,3 +262,21 @@ def prefix_tokens(tok, pos, out, B, T, tokens_per_image, D):
     check(lib.vitk_prefix_tokens(ptr(tok), ptr(pos), ptr(out), B, T, tokens_per_image, D, _stream()),
           "vitk_prefix_tokens")
     launch_count += 1
+
+
+def gemm_batched(a, lda, sa_h, sa_b, a_mn, b, ldb, sb_h, sb_b, b_mn, M, N, K, nh, nb, out, ldo, so_h, so_b,
+                 a_off=0, b_off=0, out_off=0, out_f32=False):
+    """nh*nb independent GEMMs addressed by element strides (see vitk_gemm_bf16_batched). a/b/out are the base tensors;
+    *_off are element offsets into them."""
+    global launch_count
+    _need_cuda(a, b, out)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    lib = _lib.load()
+    osz = 4 if out_f32 else 2
+    rc = lib.vitk_gemm_bf16_batched(a.data_ptr() + 2 * a_off, lda, sa_h, sa_b, int(a_mn), b.data_ptr() + 2 * b_off, ldb,
+                                    sb_h, sb_b, int(b_mn), M, N, K, nh, nb,
+                                    EPI_STORE_F32 if out_f32 else EPI_STORE_BF16, out.data_ptr() + osz * out_off, ldo,
+                                    so_h, so_b, _stream())
+    check(rc, "vitk_gemm_bf16_batched")
+    launch_count += 1
+    return out
