@@ -147,6 +147,30 @@ int vitk_attn_fwd(const void* qkv_bf16, void* out_bf16, float* lse2, int B, int 
 int vitk_attn_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2, float* delta,
                   void* dqkv_bf16, int B, int N, int H, int d, float scale, void* stream);
 
+/*
+ * CaiT talking-heads mixing (models/cait.py:116-125), forward: S fp32 [B,H,N,Np] (raw q.k logits, row pitch Np >= N,
+ * Np % 8 == 0) -> Pm bf16 [B,H,N,Np] = Ww softmax_j(scale*Wl S + bl) + bw (pad columns zero); rowmax/rowsum fp32
+ * [B,H,N] are saved for backward. wl/ww fp32 [H,H] (= proj_l.weight / proj_w.weight), bl/bw fp32 [H]. H in {2,4,6,8,16}.
+ */
+int vitk_th_mix_fwd(const float* S, const float* wl, const float* bl, const float* ww, const float* bw, float scale,
+                    void* Pm_bf16, float* rowmax, float* rowsum, int B, int H, int N, int Np, void* stream);
+/* Backward of the above: dPm fp32 [B,H,N,Np] -> dS bf16 [B,H,N,Np] (gradient w.r.t. the RAW logits, i.e. scale folded
+ * in); dwl/dbl/dww/dbw are accumulated (+=). */
+int vitk_th_mix_bwd(const float* S, const float* dPm, const float* rowmax, const float* rowsum, const float* wl,
+                    const float* bl, const float* ww, const float* bw, float scale, void* dS_bf16, float* dwl, float* dbl,
+                    float* dww, float* dbw, int B, int H, int N, int Np, void* stream);
+
+/*
+ * CaiT class attention (models/cait.py:38-55): one query row per (image, head). q bf16 [B,C] (unscaled), keys/values:
+ * row 0 = class token kc/vc bf16 [B, ldc], rows 1..n = patch tokens kx/vx bf16 [B*n, ldkv]. out bf16 [B,C];
+ * p fp32 [B,H,n+1] (softmax probabilities, saved for backward). d = C/H in {48, 64}.
+ */
+int vitk_class_attn_fwd(const void* q, const void* kc, const void* kx, const void* vc, const void* vx, long long ldkv,
+                        long long ldc, float scale, void* out, float* p, int B, int H, int n, int d, void* stream);
+int vitk_class_attn_bwd(const void* q, const void* kc, const void* kx, const void* vc, const void* vx, long long ldkv,
+                        long long ldc, const float* p, const void* dout, float scale, void* dq, void* dkc, void* dkx,
+                        void* dvc, void* dvx, long long lddkv, long long lddc, int B, int H, int n, int d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,13 +35,21 @@ def import_reference_cait():
     lay = types.ModuleType("timm.models.layers")
     lay.trunc_normal_ = ovit.trunc_normal_
     lay.DropPath = ovit.DropPath
-    for name, mod in [("timm", tm), ("timm.models", tmm), ("timm.models.vision_transformer", vt),
-                      ("timm.models.registry", reg), ("timm.models.layers", lay)]:
-        sys.modules.setdefault(name, mod)
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("reference_cait", os.path.join(REF, "models", "cait.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
+    stubs = {"timm": tm, "timm.models": tmm, "timm.models.vision_transformer": vt, "timm.models.registry": reg,
+             "timm.models.layers": lay}
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)          # force the oracle-backed stubs even if another timm (or shim) is loaded
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("reference_cait", os.path.join(REF, "models", "cait.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
     return mod
 
 

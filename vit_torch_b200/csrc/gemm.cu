@@ -56,6 +56,7 @@ static int dispatch_gemm(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, co
     VITK_CASE(0, 1, EPI_STORE_BF16)
     VITK_CASE(0, 1, EPI_DGELU)
     VITK_CASE(0, 1, EPI_STORE_F32)
+    VITK_CASE(0, 1, EPI_RESID_F32)
     // wgrad: dY^T and X^T, both MN-major, split-K accumulate
     VITK_CASE(1, 1, EPI_ATOMIC_F32)
     VITK_CASE(1, 1, EPI_STORE_F32)

@@ -68,7 +68,7 @@ class BlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, num_heads, eps, scale, rowscale, n1w, n1b, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b,
-                fc2w, fc2b, g1, g2):
+                fc2w, fc2b, g1, g2, thl_w=None, thl_b=None, thw_w=None, thw_b=None):
         B, N, D = x.shape
         M = B * N
         H = num_heads
@@ -82,7 +82,23 @@ class BlockFn(torch.autograd.Function):
         h1, mean1, rstd1 = ops.layernorm_fwd(x0, n1w, n1b, eps)
         qkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
         ops.gemm(h1, wqkv, epilogue=ops.EPI_STORE_BF16, bias=qkvb, out=qkv)
-        o, lse2 = ops.attn_fwd(qkv, B, N, H, d, scale)
+        th = thl_w is not None
+        S = Pm = rmax = rsum = lse2 = None
+        if not th:
+            o, lse2 = ops.attn_fwd(qkv, B, N, H, d, scale)
+        else:
+            # talking-heads attention (models/cait.py:111-128): raw logits by a batched tcgen05 GEMM reading q/k in
+            # place, one fused mixing/softmax/mixing pass, P'.V by a second batched GEMM
+            Np = (N + 7) // 8 * 8
+            S = torch.empty((B, H, N, Np), dtype=torch.float32, device=dev)
+            ops.gemm_batched(qkv, 3 * D, d, N * 3 * D, False, qkv, 3 * D, d, N * 3 * D, False, N, N, d, H, B, S, Np,
+                             N * Np, H * N * Np, a_off=0, b_off=D, out_f32=True)
+            Pm, rmax, rsum = ops.th_mix_fwd(S, thl_w, thl_b, thw_w, thw_b, scale, B, H, N, Np)
+            o = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+            ops.gemm_batched(Pm, Np, N * Np, H * N * Np, False, qkv, 3 * D, d, N * 3 * D, True, N, d, N, H, B, o, D, d,
+                             N * D, b_off=2 * D)
+            if not need_bwd:
+                S = Pm = None
         x1 = torch.empty((M, D), dtype=torch.float32, device=dev)
         f1 = torch.empty((M, D), dtype=torch.bfloat16, device=dev) if (g1 is not None and need_bwd) else None
         ops.gemm(o, wproj, epilogue=ops.EPI_RESID_F32, bias=projb, gamma=g1, resid=x0, out=x1, out2=f1,
@@ -98,16 +114,18 @@ class BlockFn(torch.autograd.Function):
 
         if need_bwd:
             ctx.save_for_backward(x0, mean1, rstd1, h1, qkv, o, lse2, x1, mean2, rstd2, h2, a, g, f1, f2, n1w, qkvw,
-                                  projw, n2w, fc1w, fc2w, g1, g2, rowscale, wqkv, wproj, wfc1, wfc2)
+                                  projw, n2w, fc1w, fc2w, g1, g2, rowscale, wqkv, wproj, wfc1, wfc2, S, Pm, rmax, rsum,
+                                  thl_w, thl_b, thw_w, thw_b)
             ctx.dims = (B, N, D, H, d, scale)
             ctx.has = (qkvb is not None, projb is not None, fc1b is not None, fc2b is not None)
-            ctx.param_refs = [n1w, n1b, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b, g1, g2]
+            ctx.param_refs = [n1w, n1b, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b, g1, g2, thl_w,
+                              thl_b, thw_w, thw_b]
         return x2.view(B, N, D)
 
     @staticmethod
     def backward(ctx, dout):
         (x0, mean1, rstd1, h1, qkv, o, lse2, x1, mean2, rstd2, h2, a, g, f1, f2, n1w, qkvw, projw, n2w, fc1w, fc2w,
-         g1, g2, rowscale, wqkv, wproj, wfc1, wfc2) = ctx.saved_tensors
+         g1, g2, rowscale, wqkv, wproj, wfc1, wfc2, S, Pm, rmax, rsum, thl_w, thl_b, thw_w, thw_b) = ctx.saved_tensors
         B, N, D, H, d, scale = ctx.dims
         M = B * N
         dev = dout.device
@@ -116,9 +134,10 @@ class BlockFn(torch.autograd.Function):
         # parameter order of forward(): index 5.. = n1w n1b qkvw qkvb projw projb n2w n2b fc1w fc1b fc2w fc2b g1 g2
         shapes_like = [n1w, n1w, qkvw, qkvw[:, 0] if ctx.has[0] else None, projw, projw[:, 0] if ctx.has[1] else None,
                        n2w, n2w, fc1w, fc1w[:, 0] if ctx.has[2] else None, fc2w, fc2w[:, 0] if ctx.has[3] else None,
-                       g1, g2]
-        buf, gv = _flat_grads(shapes_like, needs[5:19], dev)
-        (dn1w, dn1b, dqkvw, dqkvb, dprojw, dprojb, dn2w, dn2b, dfc1w, dfc1b, dfc2w, dfc2b, dg1, dg2) = gv
+                       g1, g2, thl_w, thl_b, thw_w, thw_b]
+        buf, gv = _flat_grads(shapes_like, needs[5:23], dev)
+        (dn1w, dn1b, dqkvw, dqkvb, dprojw, dprojb, dn2w, dn2b, dfc1w, dfc1b, dfc2w, dfc2b, dg1, dg2, dthl_w, dthl_b,
+         dthw_w, dthw_b) = gv
 
         dy = dout if dout.is_contiguous() else dout.contiguous()
         dx2 = dy.view(M, D)
@@ -156,7 +175,33 @@ class BlockFn(torch.autograd.Function):
             ops.gemm(dx1b, o, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dprojw)
         if dprojb is not None:
             ops.colsum_accum(dx1b, dprojb)
-        dqkv = ops.attn_bwd(qkv, o, do, lse2, B, N, H, d, scale)
+        if thl_w is None:
+            dqkv = ops.attn_bwd(qkv, o, do, lse2, B, N, H, d, scale)
+        else:
+            Np = S.shape[-1]
+            zeros = lambda t: torch.zeros_like(t, dtype=torch.float32)
+            dthl_w = dthl_w if dthl_w is not None else zeros(thl_w)
+            dthl_b = dthl_b if dthl_b is not None else zeros(thl_b)
+            dthw_w = dthw_w if dthw_w is not None else zeros(thw_w)
+            dthw_b = dthw_b if dthw_b is not None else zeros(thw_b)
+            dPm = torch.empty((B, H, N, Np), dtype=torch.float32, device=dev)      # dP'[i,j] = dO_i . v_j
+            ops.gemm_batched(do, D, d, N * D, False, qkv, 3 * D, d, N * 3 * D, False, N, N, d, H, B, dPm, Np, N * Np,
+                             H * N * Np, b_off=2 * D, out_f32=True)
+            dqkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
+            ops.gemm_batched(Pm, Np, N * Np, H * N * Np, True, do, D, d, N * D, True, N, d, N, H, B, dqkv, 3 * D, d,
+                             N * 3 * D, out_off=2 * D)                              # dV = P'^T dO
+            dS = ops.th_mix_bwd(S, dPm, rmax, rsum, thl_w, thl_b, thw_w, thw_b, scale, dthl_w, dthl_b, dthw_w, dthw_b,
+                                B, H, N, Np)
+            del dPm
+            ops.gemm_batched(dS, Np, N * Np, H * N * Np, False, qkv, 3 * D, d, N * 3 * D, True, N, d, N, H, B, dqkv,
+                             3 * D, d, N * 3 * D, b_off=D, out_off=0)               # dQ = dS K
+            ops.gemm_batched(dS, Np, N * Np, H * N * Np, True, qkv, 3 * D, d, N * 3 * D, True, N, d, N, H, B, dqkv,
+                             3 * D, d, N * 3 * D, b_off=0, out_off=D)               # dK = dS^T Q
+            del dS
+            if not needs[19]: dthl_w = None
+            if not needs[20]: dthl_b = None
+            if not needs[21]: dthw_w = None
+            if not needs[22]: dthw_b = None
         dh1 = do
         ops.gemm(dqkv, wqkv, b_mn=True, epilogue=ops.EPI_STORE_BF16, out=dh1)
         if dqkvw is not None:
@@ -174,7 +219,7 @@ class BlockFn(torch.autograd.Function):
             for hook in grad_bucket_hooks:
                 hook(buf, ctx.param_refs, alias)
         return (dx, None, None, None, None, dn1w, dn1b, dqkvw, dqkvb, dprojw, dprojb, dn2w, dn2b, dfc1w, dfc1b,
-                dfc2w, dfc2b, dg1, dg2)
+                dfc2w, dfc2b, dg1, dg2, dthl_w, dthl_b, dthw_w, dthw_b)
 
 
 # callbacks(flat_grad_buffer, params, grad_views) fired when one block's parameter gradients are complete (used by dist.py)
@@ -256,3 +301,138 @@ class TokenNormFn(torch.autograd.Function):
         ops.layernorm_bwd_rows(dy, xc.view(-1)[tok * D:], N * D, B, D, w, mean, rstd, dx=dx.view(-1)[tok * D:],
                                dx_stride=N * D, dweight=dw, dbias=db)
         return dx, dw, db, None, None
+
+
+class ClassAttnBlockFn(torch.autograd.Function):
+    """CaiT LayerScale_Block_CA (models/cait.py:75-84):
+         u = cat(cls, x); cls += g1 * ClassAttn(LN1 u); cls += g2 * Mlp(LN2 cls)
+    x [B, n, C] fp32 (patch tokens, unchanged), cls [B, 1, C] fp32 -> new cls [B, 1, C] fp32.
+    No concatenation is materialised: LN1 runs on the patch rows and on the class rows separately and the class-
+    attention kernel takes the class row and the patch rows of K / V through two pointers. K and V come from one
+    tcgen05 GEMM against the stacked [Wk; Wv] weight (one dgrad, one wgrad)."""
+
+    @staticmethod
+    def forward(ctx, x, cls, num_heads, eps, scale, n1w, n1b, qw, qb, kw, kb, vw, vb, projw, projb, n2w, n2b, fc1w,
+                fc1b, fc2w, fc2b, g1, g2):
+        B, n, C = x.shape
+        H = num_heads
+        d = C // H
+        dev = x.device
+        xr = x.contiguous().view(B * n, C)
+        c0 = cls.contiguous().view(B, C)
+        need_bwd = any(ctx.needs_input_grad)
+        wq, wp, w1, w2 = bf16_weight(qw), bf16_weight(projw), bf16_weight(fc1w), bf16_weight(fc2w)
+        wkv = torch.empty((2 * C, C), dtype=torch.bfloat16, device=dev)
+        ops.cast_bf16(kw.detach(), out=wkv[:C])
+        ops.cast_bf16(vw.detach(), out=wkv[C:])
+        bkv = None
+        if kb is not None:
+            bkv = torch.cat((kb.detach(), vb.detach()))
+        hidden = fc1w.shape[0]
+
+        hx, mx, rx = ops.layernorm_fwd(xr, n1w, n1b, eps)
+        hc, mc, rc = ops.layernorm_fwd(c0, n1w, n1b, eps)
+        q = torch.empty((B, C), dtype=torch.bfloat16, device=dev)
+        ops.gemm(hc, wq, epilogue=ops.EPI_STORE_BF16, bias=qb, out=q)
+        kvx = torch.empty((B * n, 2 * C), dtype=torch.bfloat16, device=dev)
+        ops.gemm(hx, wkv, epilogue=ops.EPI_STORE_BF16, bias=bkv, out=kvx)
+        kvc = torch.empty((B, 2 * C), dtype=torch.bfloat16, device=dev)
+        ops.gemm(hc, wkv, epilogue=ops.EPI_STORE_BF16, bias=bkv, out=kvc)
+        kc, vc = kvc[:, :C], kvc[:, C:]   # strided views (pitch 2C), read in place
+        a, p = ops.class_attn_fwd(q, kc, kvx[:, :C], vc, kvx[:, C:], 2 * C, 2 * C, scale, B, H, n, d)
+        c1 = torch.empty((B, C), dtype=torch.float32, device=dev)
+        f1 = torch.empty((B, C), dtype=torch.bfloat16, device=dev) if need_bwd else None
+        ops.gemm(a, wp, epilogue=ops.EPI_RESID_F32, bias=projb, gamma=g1, resid=c0, out=c1, out2=f1)
+        h2, m2, r2 = ops.layernorm_fwd(c1, n2w, n2b, eps)
+        pre = torch.empty((B, hidden), dtype=torch.bfloat16, device=dev) if need_bwd else None
+        act = torch.empty((B, hidden), dtype=torch.bfloat16, device=dev)
+        ops.gemm(h2, w1, epilogue=ops.EPI_BIAS_GELU, bias=fc1b, out=pre, out2=act)
+        c2 = torch.empty((B, C), dtype=torch.float32, device=dev)
+        f2 = torch.empty((B, C), dtype=torch.bfloat16, device=dev) if need_bwd else None
+        ops.gemm(act, w2, epilogue=ops.EPI_RESID_F32, bias=fc2b, gamma=g2, resid=c1, out=c2, out2=f2)
+        if need_bwd:
+            ctx.save_for_backward(xr, c0, hx, mx, rx, hc, mc, rc, q, kvx, kvc, a, p, c1, f1, h2, m2, r2, pre, act, f2,
+                                  n1w, qw, kw, vw, projw, n2w, fc1w, fc2w, g1, g2, wq, wkv, wp, w1, w2)
+            ctx.dims = (B, n, C, H, d, scale)
+            ctx.has = (qb is not None, kb is not None, projb is not None, fc1b is not None, fc2b is not None)
+            ctx.param_refs = [n1w, n1b, qw, qb, kw, kb, vw, vb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b, g1, g2]
+        return c2.view(B, 1, C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (xr, c0, hx, mx, rx, hc, mc, rc, q, kvx, kvc, a, p, c1, f1, h2, m2, r2, pre, act, f2, n1w, qw, kw, vw, projw,
+         n2w, fc1w, fc2w, g1, g2, wq, wkv, wp, w1, w2) = ctx.saved_tensors
+        B, n, C, H, d, scale = ctx.dims
+        dev = dout.device
+        hidden = fc1w.shape[0]
+        needs = ctx.needs_input_grad
+        has_qb, has_kb, has_pb, has_b1, has_b2 = ctx.has
+        vec = n1w
+        like = [n1w, n1w, qw, vec if has_qb else None, kw, vec if has_kb else None, vw, vec if has_kb else None, projw,
+                vec if has_pb else None, n2w, n2w, fc1w, fc1w[:, 0] if has_b1 else None, fc2w, vec if has_b2 else None,
+                g1, g2]
+        buf, gv = _flat_grads(like, needs[5:23], dev)
+        (dn1w, dn1b, dqw, dqb, dkw, dkb, dvw, dvb, dprojw, dprojb, dn2w, dn2b, dfc1w, dfc1b, dfc2w, dfc2b, dg1, dg2) = gv
+        dc2 = dout.contiguous().view(B, C).float()
+        # ---- Mlp on the class token
+        if dg2 is not None:
+            ops.colsum_prod_accum(dc2, f2, dg2)
+        dc2b = ops.scale_cast(dc2, B, C, colscale=g2)
+        dact = torch.empty((B, hidden), dtype=torch.bfloat16, device=dev)
+        ops.gemm(dc2b, w2, b_mn=True, epilogue=ops.EPI_DGELU, aux=pre, out=dact)
+        if dfc2w is not None:
+            ops.gemm(dc2b, act, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dfc2w)
+        if dfc2b is not None:
+            ops.colsum_accum(dc2b, dfc2b)
+        dh2 = torch.empty((B, C), dtype=torch.bfloat16, device=dev)
+        ops.gemm(dact, w1, b_mn=True, epilogue=ops.EPI_STORE_BF16, out=dh2)
+        if dfc1w is not None:
+            ops.gemm(dact, h2, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dfc1w)
+        if dfc1b is not None:
+            ops.colsum_accum(dact, dfc1b)
+        dc1, _ = ops.layernorm_bwd(dh2, c1, n2w, m2, r2, dres=dc2, dweight=dn2w, dbias=dn2b)
+        # ---- class attention
+        if dg1 is not None:
+            ops.colsum_prod_accum(dc1, f1, dg1)
+        dc1b = ops.scale_cast(dc1, B, C, colscale=g1)
+        da = torch.empty((B, C), dtype=torch.bfloat16, device=dev)
+        ops.gemm(dc1b, wp, b_mn=True, epilogue=ops.EPI_STORE_BF16, out=da)
+        if dprojw is not None:
+            ops.gemm(dc1b, a, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dprojw)
+        if dprojb is not None:
+            ops.colsum_accum(dc1b, dprojb)
+        dq = torch.empty((B, C), dtype=torch.bfloat16, device=dev)
+        dkvx = torch.empty((B * n, 2 * C), dtype=torch.bfloat16, device=dev)
+        dkvc = torch.empty((B, 2 * C), dtype=torch.bfloat16, device=dev)
+        ops.class_attn_bwd(q, kvc[:, :C], kvx[:, :C], kvc[:, C:], kvx[:, C:], 2 * C, 2 * C, p, da, scale, dq,
+                           dkvc[:, :C], dkvx[:, :C], dkvc[:, C:], dkvx[:, C:], 2 * C, 2 * C, B, H, n, d)
+        # ---- q / k / v Linears: dgrad to the LN1 outputs, wgrad into the stacked [dWk; dWv] view of the flat buffer
+        dhx = torch.empty((B * n, C), dtype=torch.bfloat16, device=dev)
+        ops.gemm(dkvx, wkv, b_mn=True, epilogue=ops.EPI_STORE_BF16, out=dhx)
+        dhc32 = torch.empty((B, C), dtype=torch.float32, device=dev)
+        ops.gemm(dkvc, wkv, b_mn=True, epilogue=ops.EPI_STORE_F32, out=dhc32)
+        dhc32b = torch.empty((B, C), dtype=torch.float32, device=dev)
+        ops.gemm(dq, wq, b_mn=True, epilogue=ops.EPI_RESID_F32, resid=dhc32, out=dhc32b)
+        for dw, dy_sl, in ((dkw, slice(0, C)), (dvw, slice(C, 2 * C))):
+            if dw is not None:
+                ops.gemm(dkvx[:, dy_sl], hx, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dw)
+                ops.gemm(dkvc[:, dy_sl], hc, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dw)
+        for db, dy_sl in ((dkb, slice(0, C)), (dvb, slice(C, 2 * C))):
+            if db is not None:
+                ops.colsum_accum(dkvx[:, dy_sl], db)
+                ops.colsum_accum(dkvc[:, dy_sl], db)
+        if dqw is not None:
+            ops.gemm(dq, hc, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dqw)
+        if dqb is not None:
+            ops.colsum_accum(dq, dqb)
+        # ---- LN1 backward: patch rows (gradient of x) and class rows (+ residual path of cls)
+        dx, _ = ops.layernorm_bwd(dhx, xr, n1w, mx, rx, dweight=dn1w, dbias=dn1b)
+        dcls = torch.empty((B, C), dtype=torch.float32, device=dev)
+        ops.layernorm_bwd_rows(dhc32b, c0, C, B, C, n1w, mc, rc, dres=dc1, dx=dcls, dx_stride=C, dweight=dn1w,
+                               dbias=dn1b)
+        if grad_bucket_hooks:
+            alias = [None if v is None else v.view(v.shape) for v in gv]
+            for hook in grad_bucket_hooks:
+                hook(buf, ctx.param_refs, alias)
+        return (dx.view(B, n, C), dcls.view(B, 1, C), None, None, None, dn1w, dn1b, dqw, dqb, dkw, dkb, dvw, dvb, dprojw,
+                dprojb, dn2w, dn2b, dfc1w, dfc1b, dfc2w, dfc2b, dg1, dg2)

@@ -90,7 +90,7 @@ class Block(nn.Module):
         return Fn.BlockFn.apply(x, a.num_heads, self.norm1.eps, a.scale, rs, self.norm1.weight, self.norm1.bias,
                                 a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias, self.norm2.weight,
                                 self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.gamma_1,
-                                self.gamma_2)
+                                self.gamma_2, None, None, None, None)
 
 
 class PatchEmbed(nn.Module):

@@ -280,3 +280,52 @@ def gemm_batched(a, lda, sa_h, sa_b, a_mn, b, ldb, sb_h, sb_b, b_mn, M, N, K, nh
     check(rc, "vitk_gemm_bf16_batched")
     launch_count += 1
     return out
+
+
+def th_mix_fwd(S, wl, bl, ww, bw, scale, B, H, N, Np):
+    """Talking-heads mixing forward. S fp32 [B,H,N,Np] -> (Pm bf16 [B,H,N,Np], rowmax, rowsum fp32 [B,H,N])."""
+    global launch_count
+    _need_cuda(S, wl, bl, ww, bw)
+    Pm = torch.empty((B, H, N, Np), dtype=torch.bfloat16, device=S.device)
+    rmax = torch.empty((B, H, N), dtype=torch.float32, device=S.device)
+    rsum = torch.empty((B, H, N), dtype=torch.float32, device=S.device)
+    lib = _lib.load()
+    check(lib.vitk_th_mix_fwd(ptr(S), ptr(wl), ptr(bl), ptr(ww), ptr(bw), scale, ptr(Pm), ptr(rmax), ptr(rsum), B, H, N,
+                              Np, _stream()), "vitk_th_mix_fwd")
+    launch_count += 1
+    return Pm, rmax, rsum
+
+
+def th_mix_bwd(S, dPm, rmax, rsum, wl, bl, ww, bw, scale, dwl, dbl, dww, dbw, B, H, N, Np):
+    """Talking-heads mixing backward -> dS bf16 [B,H,N,Np]; accumulates into dwl/dbl/dww/dbw."""
+    global launch_count
+    _need_cuda(S, dPm)
+    dS = torch.empty((B, H, N, Np), dtype=torch.bfloat16, device=S.device)
+    lib = _lib.load()
+    check(lib.vitk_th_mix_bwd(ptr(S), ptr(dPm), ptr(rmax), ptr(rsum), ptr(wl), ptr(bl), ptr(ww), ptr(bw), scale, ptr(dS),
+                              ptr(dwl), ptr(dbl), ptr(dww), ptr(dbw), B, H, N, Np, _stream()), "vitk_th_mix_bwd")
+    launch_count += 1
+    return dS
+
+
+def class_attn_fwd(q, kc, kx, vc, vx, ldkv, ldc, scale, B, H, n, d):
+    """Class attention forward -> (out bf16 [B, H*d], p fp32 [B, H, n+1])."""
+    global launch_count
+    _need_cuda(q, kc, kx, vc, vx)
+    out = torch.empty((B, H * d), dtype=torch.bfloat16, device=q.device)
+    p = torch.empty((B, H, n + 1), dtype=torch.float32, device=q.device)
+    lib = _lib.load()
+    check(lib.vitk_class_attn_fwd(ptr(q), ptr(kc), ptr(kx), ptr(vc), ptr(vx), ldkv, ldc, scale, ptr(out), ptr(p), B, H, n, d,
+                                  _stream()), "vitk_class_attn_fwd")
+    launch_count += 1
+    return out, p
+
+
+def class_attn_bwd(q, kc, kx, vc, vx, ldkv, ldc, p, dout, scale, dq, dkc, dkx, dvc, dvx, lddkv, lddc, B, H, n, d):
+    global launch_count
+    _need_cuda(q, dout)
+    lib = _lib.load()
+    check(lib.vitk_class_attn_bwd(ptr(q), ptr(kc), ptr(kx), ptr(vc), ptr(vx), ldkv, ldc, ptr(p), ptr(dout), scale,
+                                  ptr(dq), ptr(dkc), ptr(dkx), ptr(dvc), ptr(dvx), lddkv, lddc, B, H, n, d, _stream()),
+          "vitk_class_attn_bwd")
+    launch_count += 1
