@@ -242,6 +242,22 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) 
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
+// explicit shared-space vector access (32-bit shared addresses): keeps the compiler from falling back to generic
+// LD/ST when the address space of a carved-up dynamic smem pointer is not provable
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
+    return r;
+}
+__device__ __forceinline__ void sts_u4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts_f1(uint32_t saddr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // global memory vector access
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {

@@ -90,14 +90,12 @@ __device__ __forceinline__ void epi_fetch(const GemmArgs& g, EpiOperand& op, lon
 }
 
 template <int EPI>
-__device__ __forceinline__ void epi_apply(const GemmArgs& g, float4 v, long long row, int col, const float* sbias,
-                                          const float* sgamma, const EpiOperand& op, long long ooff) {
+__device__ __forceinline__ void epi_apply(const GemmArgs& g, float4 v, long long row, int col, const float4 b,
+                                          const float4 gm, const EpiOperand& op, long long ooff) {
+    // b / gm: bias and LayerScale gamma of these 4 columns (zeros / ones when absent)
     if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32 ||
                   EPI == EPI_TOKENS_F32) {
-        if (g.bias != nullptr) {
-            const float4 b = *reinterpret_cast<const float4*>(sbias);
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-        }
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
     }
     if constexpr (EPI == EPI_STORE_BF16) {
         *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + ooff + row * g.ldo + col) =
@@ -112,10 +110,7 @@ __device__ __forceinline__ void epi_apply(const GemmArgs& g, float4 v, long long
         if (g.out2 != nullptr)
             *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out2) + row * g.ldo2 + col) =
                 make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-        if (g.gamma != nullptr) {
-            const float4 gm = *reinterpret_cast<const float4*>(sgamma);
-            v.x *= gm.x; v.y *= gm.y; v.z *= gm.z; v.w *= gm.w;
-        }
+        v.x *= gm.x; v.y *= gm.y; v.z *= gm.z; v.w *= gm.w;
         if (g.rowscale != nullptr) {
             const float rs = __ldg(g.rowscale + row / g.rows_per_sample);
             v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
@@ -287,22 +282,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const long long ooff = (long long)(batch % g.nbatch_h) * g.so_h + (long long)(batch / g.nbatch_h) * g.so_b;
             float* sb = svec + as * 2 * BN;  // buffer index follows the accumulator stage (alternates per tile)
             float* sg = sb + BN;
-            if constexpr (kUsesVec) {
+            const bool use_vec = kUsesVec && (g.bias != nullptr || g.gamma != nullptr);
+            if (use_vec) {
                 // stage bias / gamma of this N tile in shared memory while the mainloop is still running
-                if (g.bias != nullptr || g.gamma != nullptr) {
-                    if (et < BN) {
-                        const int cidx = n_tile * BN + et;
-                        if (g.bias != nullptr) sb[et] = (cidx < g.N) ? __ldg(g.bias + cidx) : 0.f;
-                        if (g.gamma != nullptr) sg[et] = (cidx < g.N) ? __ldg(g.gamma + cidx) : 0.f;
-                    }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (et < BN) {
+                    const int cidx = n_tile * BN + et;
+                    sts_f1(smem_u32(sb + et), (g.bias != nullptr && cidx < g.N) ? __ldg(g.bias + cidx) : 0.f);
+                    sts_f1(smem_u32(sg + et), (g.gamma != nullptr && cidx < g.N) ? __ldg(g.gamma + cidx) : 1.f);
                 }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             // coalesced-domain coordinates of this lane: 8 rows per pass, 4 lanes x 4 columns per row
             const long long row_base = (long long)m_tile * GEMM_BM + quarter * 32;
             const int n0 = n_tile * BN + half * COLS_PER_WARP;
             const int sub_row = lane >> 2, sub_col = (lane & 3) * 4;
-            float* stg = sstage + ew * (32 * 16);
+            const uint32_t stg = smem_u32(sstage + ew * (32 * 16));
+            const uint32_t sb_addr = smem_u32(sb), sg_addr = smem_u32(sg);
             constexpr int NCHUNK = COLS_PER_WARP / 16;
             EpiOperand nxt[4];
             auto fetch_chunk = [&](int c) {
@@ -332,21 +327,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 // XOR-swizzled with (row >> 1) so that both the row-wise writes and the 8-row reads are conflict free.
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    *reinterpret_cast<uint4*>(stg + lane * 16 + ((u ^ (lane >> 1)) & 3) * 4) =
-                        make_uint4(r[u * 4 + 0], r[u * 4 + 1], r[u * 4 + 2], r[u * 4 + 3]);
+                    sts_u4(stg + (lane * 16 + ((u ^ (lane >> 1)) & 3) * 4) * 4, r[u * 4 + 0], r[u * 4 + 1], r[u * 4 + 2],
+                           r[u * 4 + 3]);
                 __syncwarp();
+                // batch every shared-memory read of the chunk before the math / global stores (2 warps per scheduler
+                // cannot hide a load-use chain per element)
+                const int lc = half * COLS_PER_WARP + c * 16 + sub_col;  // column within the N tile
+                float4 v[4];
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int lr = it * 8 + sub_row;
+                    v[it] = lds_f4(stg + (lr * 16 + (((lane & 3) ^ (lr >> 1)) & 3) * 4) * 4);
+                }
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (use_vec) {
+                    b4 = lds_f4(sb_addr + lc * 4);
+                    g4 = lds_f4(sg_addr + lc * 4);
+                }
                 EpiOperand cur[4];
 #pragma unroll
                 for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
                 if (c + 1 < NCHUNK) fetch_chunk(c + 1);
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
-                    const int lr = it * 8 + sub_row;
-                    const float4 v = *reinterpret_cast<const float4*>(stg + lr * 16 + (((lane & 3) ^ (lr >> 1)) & 3) * 4);
-                    const long long rr = row_base + lr;
+                    const long long rr = row_base + it * 8 + sub_row;
                     const int col = n0 + c * 16 + sub_col;
-                    const int lc = half * COLS_PER_WARP + c * 16 + sub_col;  // column within the N tile
-                    if (rr < g.M && col + 4 <= g.N) epi_apply<EPI>(g, v, rr, col, sb + lc, sg + lc, cur[it], ooff);
+                    if (rr < g.M && col + 4 <= g.N) epi_apply<EPI>(g, v[it], rr, col, b4, g4, cur[it], ooff);
                 }
                 __syncwarp();
             }

@@ -436,3 +436,83 @@ class ClassAttnBlockFn(torch.autograd.Function):
                 hook(buf, ctx.param_refs, alias)
         return (dx.view(B, n, C), dcls.view(B, 1, C), None, None, None, dn1w, dn1b, dqw, dqb, dkw, dkb, dvw, dvb, dprojw,
                 dprojb, dn2w, dn2b, dfc1w, dfc1b, dfc2w, dfc2b, dg1, dg2)
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class HeadFn(torch.autograd.Function):
+    """The fc classifier head of models/vision_all.py:299-320: Linear(+bias)+GELU ... Linear(bias=False) on [B, F]
+    features, as a chain of tcgen05 GEMMs (bias+GELU fused in the epilogue; dgrad with GELU' fused; split-K wgrad).
+    args: x [B, F] fp32, n_layers, then (weight, bias-or-None) per layer; GELU follows every layer but the last."""
+
+    @staticmethod
+    def forward(ctx, x, n_layers, *wb):
+        B, F0 = x.shape
+        dev = x.device
+        ws, bs = wb[0::2], wb[1::2]
+        need_bwd = any(ctx.needs_input_grad)
+        h = ops.scale_cast(x.contiguous(), B, F0) if F0 % 8 == 0 else None
+        if h is None:
+            raise NotImplementedError("head input width must be a multiple of 8")
+        saved_in, saved_pre = [h], []
+        out = None
+        for i in range(n_layers):
+            w = bf16_weight(ws[i])
+            n_out, k_in = ws[i].shape
+            if k_in % 8:
+                raise NotImplementedError("head layer widths (except the last) must be multiples of 8")
+            last = i == n_layers - 1
+            if last:
+                out = torch.zeros((B, _pad8(n_out)), dtype=torch.float32, device=dev)
+                ops.gemm(h, w, N=n_out, epilogue=ops.EPI_STORE_F32, bias=bs[i], out=out)
+            else:
+                if n_out % 8:
+                    raise NotImplementedError("head layer widths (except the last) must be multiples of 8")
+                pre = torch.empty((B, n_out), dtype=torch.bfloat16, device=dev) if need_bwd else None
+                act = torch.empty((B, n_out), dtype=torch.bfloat16, device=dev)
+                ops.gemm(h, w, epilogue=ops.EPI_BIAS_GELU, bias=bs[i], out=pre, out2=act)
+                saved_pre.append(pre)
+                saved_in.append(act)
+                h = act
+        n_last = ws[-1].shape[0]
+        if need_bwd:
+            ctx.save_for_backward(*saved_in, *saved_pre, *ws)
+            ctx.meta = (B, n_layers, [b is not None for b in bs], n_last)
+        return out[:, :n_last]
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, L, has_b, n_last = ctx.meta
+        t = ctx.saved_tensors
+        ins, pres, ws = t[:L], t[L:2 * L - 1], t[2 * L - 1:]
+        dev = dout.device
+        needs = ctx.needs_input_grad
+        grads = [None] * (2 * L)
+        # dY of the last layer as a bf16 matrix with a 16-byte aligned pitch
+        dy = torch.zeros((B, _pad8(n_last)), dtype=torch.float32, device=dev)
+        dy[:, :n_last] = dout
+        dyb = ops.scale_cast(dy, B, _pad8(n_last))
+        n_cur = n_last
+        for i in range(L - 1, -1, -1):
+            w = bf16_weight(ws[i])
+            n_out, k_in = ws[i].shape
+            dyv = dyb[:, :n_out] if dyb.shape[1] != n_out else dyb
+            if needs[2 + 2 * i]:
+                dw = torch.zeros((_pad8(n_out), k_in), dtype=torch.float32, device=dev)
+                ops.gemm(dyv, ins[i], a_mn=True, b_mn=True, M=n_out, epilogue=ops.EPI_ATOMIC_F32, out=dw)
+                grads[2 * i] = dw[:n_out]
+            if has_b[i] and needs[3 + 2 * i]:
+                db = torch.zeros((_pad8(n_out),), dtype=torch.float32, device=dev)
+                ops.colsum_accum(dyb, db)
+                grads[2 * i + 1] = db[:n_out]
+            if i > 0:
+                nxt = torch.empty((B, k_in), dtype=torch.bfloat16, device=dev)
+                ops.gemm(dyv, w, b_mn=True, K=n_out, epilogue=ops.EPI_DGELU, aux=pres[i - 1], out=nxt)
+                dyb = nxt
+            elif needs[0]:
+                dx = torch.empty((B, k_in), dtype=torch.float32, device=dev)
+                ops.gemm(dyv, w, b_mn=True, K=n_out, epilogue=ops.EPI_STORE_F32, out=dx)
+                return (dx, None, *grads)
+        return (None, None, *grads)
