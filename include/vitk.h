@@ -56,13 +56,15 @@ int vitk_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, 
  *   rowscale[row / rows_per_sample] multiplies the branch in VITK_EPI_RESID_F32 (DropPath: mask/keep_prob per sample,
  *   models/cait.py:67,140; identity when null);
  *   tok_n / tok_N / tok_T drive VITK_EPI_TOKENS_F32 (PatchEmbed + cls/pos assembly: `resid` = pos_embed fp32 [tok_N, ldr],
- *   models/cait.py:229-233, models/deit.py:35-42, DINO prepare_tokens).
+ *   models/cait.py:229-233, models/deit.py:35-42, DINO prepare_tokens);
+ *   colsum (optional fp32 [N], +=): column sums of the values stored to `out` by VITK_EPI_STORE_BF16 / VITK_EPI_DGELU
+ *   -- the bias gradient of the Linear whose dY this GEMM produces, without another pass over dY.
  */
 int vitk_gemm_bf16_ex(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major, int M,
                       int N, int K, int epilogue, const float* bias, const float* gamma, const float* resid,
                       long long ldr, void* out, long long ldo, void* out2, long long ldo2, const void* aux,
                       long long ldaux, int splits, const float* rowscale, int rows_per_sample, int tok_n, int tok_N,
-                      int tok_T, void* stream);
+                      int tok_T, float* colsum, void* stream);
 
 /*
  * Batched GEMM: nbatch_h * nbatch_b independent problems D_b[M,N] = A_b[M,K] * B_b[N,K]^T addressed by element strides
@@ -93,13 +95,14 @@ int vitk_layernorm_bwd(const void* dy_bf16, const float* x, const float* weight,
 
 /* Strided / fp32-output variants: x rows x_stride elements apart (final norm on the cls rows only: DINO
  * `norm(x)[:, 0]`, models/cait.py:244-246); y_bf16 and/or y_f32 [rows, D] dense. dy fp32 or bf16 [rows, D] dense;
- * dres / dx rows dx_stride apart. */
+ * dres / dx rows dx_stride apart. dxsum (optional, fp32 [D], +=) receives the column sums of the dx_bf16 copy, i.e.
+ * the bias gradient of the Linear that consumes it (saves a separate pass over dx). */
 int vitk_layernorm_fwd_ex(const float* x, long long x_stride, const float* weight, const float* bias, void* y_bf16,
                           float* y_f32, float* mean, float* rstd, long long rows, int D, float eps, void* stream);
 int vitk_layernorm_bwd_ex(const void* dy, int dy_is_f32, const float* x, long long x_stride, const float* weight,
                           const float* mean, const float* rstd, const float* dres, float* dx, long long dx_stride,
-                          void* dx_bf16, const float* colscale, float* dweight, float* dbias, long long rows, int D,
-                          void* stream);
+                          void* dx_bf16, const float* colscale, float* dweight, float* dbias, float* dxsum,
+                          long long rows, int D, void* stream);
 
 /* out[c] += sum_r x[r*ldx + c], fp32 (d_pos = sum_b dX[b,:,:], d_cls; SURVEY App. A.3 token assembly). cols % 4 == 0. */
 int vitk_colsum_f32(const float* x, long long ldx, long long rows, long long cols, float* out, void* stream);

@@ -26,10 +26,10 @@ SIGNATURES = {
     "vitk_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
     "vitk_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
     "vitk_gemm_bf16_ex": [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _L, _P, _L, _P, _L, _P, _L, _I,
-                          _P, _I, _I, _I, _I, _P],
+                          _P, _I, _I, _I, _I, _P, _P],
     "vitk_gemm_bf16_batched": [_P, _L, _L, _L, _I, _P, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _P],
     "vitk_layernorm_fwd_ex": [_P, _L, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
-    "vitk_layernorm_bwd_ex": [_P, _I, _P, _L, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _L, _I, _P],
+    "vitk_layernorm_bwd_ex": [_P, _I, _P, _L, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _L, _I, _P],
     "vitk_colsum_f32": [_P, _L, _L, _L, _P, _P],
     "vitk_colsum_prod": [_P, _L, _P, _L, _L, _I, _P, _P],
     "vitk_scale_cast": [_P, _L, _L, _L, _I, _P, _P, _L, _P, _P],

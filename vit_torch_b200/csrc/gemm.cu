@@ -79,7 +79,7 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
                      int N, int K, int epilogue, const float* bias, const float* gamma, const float* resid,
                      long long ldr, void* out, long long ldo, void* out2, long long ldo2, const void* aux,
                      long long ldaux, int splits, const float* rowscale, int rows_per_sample, int tok_n, int tok_N,
-                     int tok_T, void* stream, const GemmBatch& bt = GemmBatch()) {
+                     int tok_T, void* stream, const GemmBatch& bt = GemmBatch(), float* colsum = nullptr) {
     if (M <= 0 || N <= 0 || K <= 0) return VITK_ERR_ARG;
     if ((lda % 8) != 0 || (ldb % 8) != 0) return VITK_ERR_ARG;
     // The epilogue works on 4-column groups. N that is not a multiple of 4 is allowed for the plain store epilogues when
@@ -115,6 +115,8 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
     g.rowscale = rowscale; g.rows_per_sample = rows_per_sample;
     g.tok_n = tok_n; g.tok_N = tok_N; g.tok_T = tok_T;
     g.nbatch_h = bt.nh; g.nbatch_b = bt.nb; g.so_h = bt.so_h; g.so_b = bt.so_b;
+    g.colsum = colsum;
+    if (colsum != nullptr && !(epilogue == EPI_STORE_BF16 || epilogue == EPI_DGELU)) return VITK_ERR_UNSUPPORTED;
     if (bt.nh < 1 || bt.nb < 1) return VITK_ERR_ARG;
     if ((bt.sa_h | bt.sa_b | bt.sb_h | bt.sb_b) % 8 != 0) return VITK_ERR_ARG;
     if (bt.nh * bt.nb > 1 && (accumulate || !(epilogue == EPI_STORE_BF16 || epilogue == EPI_STORE_F32) || bias != nullptr))
@@ -151,9 +153,10 @@ extern "C" int vitk_gemm_bf16_ex(const void* A, long long lda, int a_mn_major, c
                                  const float* gamma, const float* resid, long long ldr, void* out, long long ldo,
                                  void* out2, long long ldo2, const void* aux, long long ldaux, int splits,
                                  const float* rowscale, int rows_per_sample, int tok_n, int tok_N, int tok_T,
-                                 void* stream) {
+                                 float* colsum, void* stream) {
     return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, epilogue, bias, gamma, resid, ldr, out, ldo, out2,
-                     ldo2, aux, ldaux, splits, rowscale, rows_per_sample, tok_n, tok_N, tok_T, stream);
+                     ldo2, aux, ldaux, splits, rowscale, rows_per_sample, tok_n, tok_N, tok_T, stream, GemmBatch(),
+                     colsum);
 }
 
 extern "C" int vitk_gemm_bf16_batched(const void* A, long long lda, long long sa_h, long long sa_b, int a_mn_major,

@@ -46,6 +46,7 @@ struct GemmArgs {
     int nbatch_h, nbatch_b;
     long long so_h, so_b;    // out strides (elements) per inner / outer batch index
     int a_perm[3], b_perm[3];  // tensor-map dim 1+i takes logical coordinate perm[i] (0 = row, 1 = batch_h, 2 = batch_b)
+    float* colsum;  // optional fp32 [N]: += column sums of the values stored to `out` (bias gradient of the next Linear)
 };
 
 constexpr int GEMM_BM = 128;
@@ -90,8 +91,8 @@ __device__ __forceinline__ void epi_fetch(const GemmArgs& g, EpiOperand& op, lon
 }
 
 template <int EPI>
-__device__ __forceinline__ void epi_apply(const GemmArgs& g, float4 v, long long row, int col, const float4 b,
-                                          const float4 gm, const EpiOperand& op, long long ooff) {
+__device__ __forceinline__ float4 epi_apply(const GemmArgs& g, float4 v, long long row, int col, const float4 b,
+                                            const float4 gm, const EpiOperand& op, long long ooff) {
     // b / gm: bias and LayerScale gamma of these 4 columns (zeros / ones when absent)
     if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32 ||
                   EPI == EPI_TOKENS_F32) {
@@ -132,6 +133,7 @@ __device__ __forceinline__ void epi_apply(const GemmArgs& g, float4 v, long long
         v.x += op.r.x; v.y += op.r.y; v.z += op.r.z; v.w += op.r.w;
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + (bimg * g.tok_N + g.tok_T + p) * g.ldo + col) = v;
     }
+    return v;  // the value written to `out` (for STORE_* / DGELU / ATOMIC; used by the optional column-sum reduction)
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
@@ -348,11 +350,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
                 if (c + 1 < NCHUNK) fetch_chunk(c + 1);
+                float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
                     const long long rr = row_base + it * 8 + sub_row;
                     const int col = n0 + c * 16 + sub_col;
-                    if (rr < g.M && col + 4 <= g.N) epi_apply<EPI>(g, v[it], rr, col, b4, g4, cur[it], ooff);
+                    if (rr < g.M && col + 4 <= g.N) {
+                        const float4 w = epi_apply<EPI>(g, v[it], rr, col, b4, g4, cur[it], ooff);
+                        cs.x += w.x; cs.y += w.y; cs.z += w.z; cs.w += w.w;
+                    }
+                }
+                if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_DGELU) {
+                    if (g.colsum != nullptr) {
+                        // reduce over the warp's 32 rows: lanes with equal (lane & 3) own the same 4 columns
+#pragma unroll
+                        for (int o = 4; o < 32; o <<= 1) {
+                            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o);
+                            cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+                            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o);
+                            cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+                        }
+                        const int col = n0 + c * 16 + sub_col;
+                        if (lane < 4 && col + 4 <= g.N) red_add_v4_f32(g.colsum + col, cs.x, cs.y, cs.z, cs.w);
+                    }
                 }
                 __syncwarp();
             }

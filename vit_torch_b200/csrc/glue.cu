@@ -76,21 +76,23 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long lo
               const float* __restrict__ w, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               const float* __restrict__ dres, float* __restrict__ dx, long long dx_stride,
               __nv_bfloat16* __restrict__ dx_bf16, const float* __restrict__ colscale, float* __restrict__ dweight,
-              float* __restrict__ dbias, long long rows, int D) {
-    // smem: w[Dp] | per-warp partials [LN_WARPS][2][Dp] (dweight, dbias). Keeping the partial sums and the weight in
+              float* __restrict__ dbias, float* __restrict__ dxsum, long long rows, int D) {
+    // smem: w[Dp] | per-warp partials [LN_WARPS][3][Dp] (dweight, dbias, column sums of the bf16 dx copy). Keeping the partial sums and the weight in
     // shared memory instead of registers leaves room for two 8-warp blocks per SM with all loads of a row in flight.
     constexpr int Dp = MAXC * 128;
     extern __shared__ __align__(16) float ln_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* sw = ln_smem;
-    float* pw = ln_smem + Dp + warp * 2 * Dp;
+    float* pw = ln_smem + Dp + warp * 3 * Dp;
     float* pb = pw + Dp;
+    float* px = pb + Dp;
     for (int c = threadIdx.x; c < Dp; c += LN_WARPS * 32) sw[c] = (c < D) ? w[c] : 0.f;
 #pragma unroll
     for (int i = 0; i < MAXC; ++i) {
         const int c = (i * 32 + lane) * 4;
         *reinterpret_cast<float4*>(pw + c) = make_float4(0, 0, 0, 0);
         *reinterpret_cast<float4*>(pb + c) = make_float4(0, 0, 0, 0);
+        *reinterpret_cast<float4*>(px + c) = make_float4(0, 0, 0, 0);
     }
     __syncthreads();
     const float inv_d = 1.0f / static_cast<float>(D);
@@ -155,6 +157,11 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long lo
                         o.x *= cs.x; o.y *= cs.y; o.z *= cs.z; o.w *= cs.w;
                     }
                     *reinterpret_cast<uint2*>(dx_bf16 + row * D + c) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+                    if (dxsum != nullptr) {  // bias gradient of the Linear that consumes the bf16 copy
+                        float4 ax = *reinterpret_cast<float4*>(px + c);
+                        ax.x += o.x; ax.y += o.y; ax.z += o.z; ax.w += o.w;
+                        *reinterpret_cast<float4*>(px + c) = ax;
+                    }
                 }
             }
         }
@@ -163,14 +170,16 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long lo
     __syncthreads();
     const float* part = ln_smem + Dp;
     for (int c = threadIdx.x; c < D; c += LN_WARPS * 32) {
-        float a = 0.f, bsum = 0.f;
+        float a = 0.f, bsum = 0.f, xsum = 0.f;
 #pragma unroll
         for (int k = 0; k < LN_WARPS; ++k) {
-            a += part[k * 2 * Dp + c];
-            bsum += part[k * 2 * Dp + Dp + c];
+            a += part[k * 3 * Dp + c];
+            bsum += part[k * 3 * Dp + Dp + c];
+            xsum += part[k * 3 * Dp + 2 * Dp + c];
         }
         if (dweight != nullptr) atomicAdd(dweight + c, a);
         if (dbias != nullptr) atomicAdd(dbias + c, bsum);
+        if (dxsum != nullptr) atomicAdd(dxsum + c, xsum);
     }
 }
 
@@ -384,8 +393,8 @@ extern "C" int vitk_layernorm_fwd_ex(const float* x, long long x_stride, const f
 
 static int ln_bwd_impl(const void* dy, int dy_is_f32, const float* x, long long x_stride, const float* weight,
                        const float* mean, const float* rstd, const float* dres, float* dx, long long dx_stride,
-                       void* dx_bf16, const float* colscale, float* dweight, float* dbias, long long rows, int D,
-                       void* stream) {
+                       void* dx_bf16, const float* colscale, float* dweight, float* dbias, float* dxsum, long long rows,
+                       int D, void* stream) {
     if (rows <= 0 || D <= 0 || (D % 4) != 0 || D > 1024 || (x_stride % 4) != 0 || (dx_stride % 4) != 0)
         return VITK_ERR_ARG;
     if (!dy || !x || !weight || !mean || !rstd) return VITK_ERR_ARG;
@@ -397,7 +406,7 @@ static int ln_bwd_impl(const void* dy, int dy_is_f32, const float* x, long long 
     const int chunks = (D + 127) / 128;
 #define VITK_LN_BWD_ONE(C, F)                                                                                        \
     do {                                                                                                             \
-        constexpr int smem = (1 + 2 * LN_WARPS) * (C) * 128 * 4;                                                     \
+        constexpr int smem = (1 + 3 * LN_WARPS) * (C) * 128 * 4;                                                     \
         static bool attr = false;                                                                                    \
         if (!attr) {                                                                                                 \
             if (cudaFuncSetAttribute(ln_bwd_kernel<C, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=      \
@@ -406,7 +415,7 @@ static int ln_bwd_impl(const void* dy, int dy_is_f32, const float* x, long long 
             attr = true;                                                                                             \
         }                                                                                                            \
         ln_bwd_kernel<C, F><<<grid, LN_WARPS * 32, smem, st>>>(dy, x, x_stride, weight, mean, rstd, dres, dx,        \
-                                                               dx_stride, dxb, colscale, dweight, dbias, rows, D);   \
+                                                               dx_stride, dxb, colscale, dweight, dbias, dxsum, rows, D); \
     } while (0)
 #define VITK_LN_BWD(C)                      \
     do {                                    \
@@ -426,16 +435,16 @@ extern "C" int vitk_layernorm_bwd(const void* dy_bf16, const float* x, const flo
                                   const float* rstd, const float* dres, float* dx, void* dx_bf16,
                                   const float* colscale, float* dweight, float* dbias, long long rows, int D,
                                   void* stream) {
-    return ln_bwd_impl(dy_bf16, 0, x, D, weight, mean, rstd, dres, dx, D, dx_bf16, colscale, dweight, dbias, rows, D,
-                       stream);
+    return ln_bwd_impl(dy_bf16, 0, x, D, weight, mean, rstd, dres, dx, D, dx_bf16, colscale, dweight, dbias, nullptr,
+                       rows, D, stream);
 }
 
 extern "C" int vitk_layernorm_bwd_ex(const void* dy, int dy_is_f32, const float* x, long long x_stride,
                                      const float* weight, const float* mean, const float* rstd, const float* dres,
                                      float* dx, long long dx_stride, void* dx_bf16, const float* colscale,
-                                     float* dweight, float* dbias, long long rows, int D, void* stream) {
+                                     float* dweight, float* dbias, float* dxsum, long long rows, int D, void* stream) {
     return ln_bwd_impl(dy, dy_is_f32, x, x_stride, weight, mean, rstd, dres, dx, dx_stride, dx_bf16, colscale, dweight,
-                       dbias, rows, D, stream);
+                       dbias, dxsum, rows, D, stream);
 }
 
 extern "C" int vitk_colsum_bf16(const void* x_bf16, long long ldx, long long rows, int N, float* out, void* stream) {

@@ -143,27 +143,32 @@ class BlockFn(torch.autograd.Function):
         dx2 = dy.view(M, D)
         if getattr(dout, "_vitk_bf16", None) is not None:
             dx2._vitk_bf16 = dout._vitk_bf16
+            dx2._vitk_colsum = getattr(dout, "_vitk_colsum", None)
 
         # ---- Mlp branch: x2 = x1 + g2 * rowscale * (fc2(gelu(fc1(h2))))
         if dg2 is not None:
             ops.colsum_prod_accum(dx2, f2, dg2)  # (rowscale == None whenever LayerScale models are built by the zoo)
         dx2b = _dy_bf16(dx2, M, D, g2, rowscale, N)
         da = torch.empty((M, hidden), dtype=torch.bfloat16, device=dev)
-        ops.gemm(dx2b, wfc2, b_mn=True, epilogue=ops.EPI_DGELU, aux=a, out=da)
+        # fc2 dgrad with GELU' fused; the same epilogue reduces da over rows = fc1 bias gradient
+        ops.gemm(dx2b, wfc2, b_mn=True, epilogue=ops.EPI_DGELU, aux=a, out=da, colsum=dfc1b)
         if dfc2w is not None:
             ops.gemm(dx2b, g, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dfc2w)
         if dfc2b is not None:
-            ops.colsum_accum(dx2b, dfc2b)
+            side = getattr(dx2, "_vitk_colsum", None) if dx2b is getattr(dx2, "_vitk_bf16", None) else None
+            if side is not None:
+                dfc2b.add_(side)        # column sums of dx2b were produced by the kernel that wrote dx2b
+            else:
+                ops.colsum_accum(dx2b, dfc2b)
         dh2 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
         ops.gemm(da, wfc1, b_mn=True, epilogue=ops.EPI_STORE_BF16, out=dh2)
         if dfc1w is not None:
             ops.gemm(da, h2, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dfc1w)
-        if dfc1b is not None:
-            ops.colsum_accum(da, dfc1b)
         del da
         # ---- LN2 backward + residual: dx1 = dx2 + LN2'(dh2); bf16 copy (x g1) feeds the proj dgrad/wgrad
         plain1 = g1 is None and rowscale is None
-        dx1, dx1b = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dx2, dweight=dn2w, dbias=dn2b, want_bf16=plain1)
+        dx1, dx1b = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dx2, dweight=dn2w, dbias=dn2b, want_bf16=plain1,
+                                      dxsum=dprojb if plain1 else None)
         if dg1 is not None:
             ops.colsum_prod_accum(dx1, f1, dg1)
         if not plain1:
@@ -173,7 +178,7 @@ class BlockFn(torch.autograd.Function):
         ops.gemm(dx1b, wproj, b_mn=True, epilogue=ops.EPI_STORE_BF16, out=do)
         if dprojw is not None:
             ops.gemm(dx1b, o, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dprojw)
-        if dprojb is not None:
+        if dprojb is not None and not plain1:
             ops.colsum_accum(dx1b, dprojb)
         if thl_w is None:
             dqkv = ops.attn_bwd(qkv, o, do, lse2, B, N, H, d, scale)
@@ -209,9 +214,12 @@ class BlockFn(torch.autograd.Function):
         if dqkvb is not None:
             ops.colsum_accum(dqkv, dqkvb)
         # ---- LN1 backward + residual; the bf16 copy is handed to the previous block through a side channel
-        dx0, dx0b = ops.layernorm_bwd(dh1, x0, n1w, mean1, rstd1, dres=dx1, dweight=dn1w, dbias=dn1b, want_bf16=True)
+        side_sum = torch.zeros((D,), dtype=torch.float32, device=dev)
+        dx0, dx0b = ops.layernorm_bwd(dh1, x0, n1w, mean1, rstd1, dres=dx1, dweight=dn1w, dbias=dn1b, want_bf16=True,
+                                      dxsum=side_sum)
         dx = dx0.view(B, N, D)
         dx._vitk_bf16 = dx0b
+        dx._vitk_colsum = side_sum
         if grad_bucket_hooks:
             # hand the hooks their own alias views so the returned ones stay uniquely referenced (autograd then adopts
             # them as .grad without cloning)

@@ -57,7 +57,7 @@ EPI_TOKENS_F32 = 6
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, epilogue=EPI_STORE_BF16, bias=None, gamma=None,
-         resid=None, out=None, out2=None, aux=None, splits=0, rowscale=None, rows_per_sample=0, tok=None):
+         resid=None, out=None, out2=None, aux=None, splits=0, rowscale=None, rows_per_sample=0, tok=None, colsum=None):
     """D[M,N] = A[M,K] @ B[N,K]^T with a fused epilogue. See vitk_gemm_bf16 in include/vitk.h.
 
     a: bf16 [M,K] (a_mn=False) or [K,M] (a_mn=True); b: bf16 [N,K] (b_mn=False) or [K,N] (b_mn=True).
@@ -81,7 +81,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, epilogue=EPI_S
         ptr(bias), ptr(gamma), ptr(resid), _ld(resid) if resid is not None else 0,
         ptr(out), _ld(out) if out is not None else 0, ptr(out2), _ld(out2) if out2 is not None else 0,
         ptr(aux), _ld(aux) if aux is not None else 0, splits, ptr(rowscale), rows_per_sample, tok_n, tok_N, tok_T,
-        _stream())
+        ptr(colsum), _stream())
     check(rc, "vitk_gemm_bf16_ex")
     if _gemm_events is not None:
         ev1 = torch.cuda.Event(enable_timing=True)
@@ -108,8 +108,9 @@ def layernorm_fwd(x, weight, bias, eps=1e-6):
 
 
 def layernorm_bwd(dy, x, weight, mean, rstd, *, dres=None, dweight=None, dbias=None, want_f32=True, want_bf16=False,
-                  colscale=None):
-    """Returns (dx_f32 or None, dx_bf16 or None); accumulates into dweight/dbias (fp32 [D]) when given."""
+                  colscale=None, dxsum=None):
+    """Returns (dx_f32 or None, dx_bf16 or None); accumulates into dweight/dbias (fp32 [D]) when given, and the column
+    sums of the bf16 copy into dxsum."""
     global launch_count
     _need_cuda(dy, x)
     assert dy.dtype == torch.bfloat16 and dy.is_contiguous() and x.is_contiguous()
@@ -117,8 +118,9 @@ def layernorm_bwd(dy, x, weight, mean, rstd, *, dres=None, dweight=None, dbias=N
     dx = torch.empty_like(x) if want_f32 else None
     dxb = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
     lib = _lib.load()
-    check(lib.vitk_layernorm_bwd(ptr(dy), ptr(x), ptr(weight), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(dxb),
-                                 ptr(colscale), ptr(dweight), ptr(dbias), rows, D, _stream()), "vitk_layernorm_bwd")
+    check(lib.vitk_layernorm_bwd_ex(ptr(dy), 0, ptr(x), D, ptr(weight), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), D,
+                                    ptr(dxb), ptr(colscale), ptr(dweight), ptr(dbias), ptr(dxsum), rows, D, _stream()),
+          "vitk_layernorm_bwd_ex")
     launch_count += 1
     return dx, dxb
 
@@ -200,7 +202,7 @@ def layernorm_bwd_rows(dy, x, x_stride, rows, D, weight, mean, rstd, *, dres=Non
     lib = _lib.load()
     check(lib.vitk_layernorm_bwd_ex(ptr(dy), int(dy.dtype == torch.float32), ptr(x), x_stride, ptr(weight), ptr(mean),
                                     ptr(rstd), ptr(dres), ptr(dx), dx_stride if dx_stride is not None else D,
-                                    ptr(dx_bf16), ptr(colscale), ptr(dweight), ptr(dbias), rows, D, _stream()),
+                                    ptr(dx_bf16), ptr(colscale), ptr(dweight), ptr(dbias), None, rows, D, _stream()),
           "vitk_layernorm_bwd_ex")
     launch_count += 1
 
