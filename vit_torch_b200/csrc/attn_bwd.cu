@@ -180,6 +180,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
         }
         uint8_t* ds_row = smem + DQ_SMEM_DS + row * 128;
         const int sw = row & 7;
+        const float rscale = row_ok ? a.scale : 0.f;  // rows beyond N contribute nothing
         for (int j = 0; j < nkv; ++j) {
             const int valid = min(64, a.N - j * 64);
             mbar_wait(sdp_full, j & 1);
@@ -192,11 +193,19 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
                 tmem_ld_32x32b_x32(tmem_dp + lane_off + c * 32, dpr);
                 tmem_ld_wait();
                 float ds[32];
+                if (c * 32 + 32 <= valid) {  // warp-uniform: no per-element masking in fully valid chunks
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float p = exp2f(fmaf(__uint_as_float(sr[i]), a.scale_log2, -lse2));
-                    const float v = a.scale * p * (__uint_as_float(dpr[i]) - delta);
-                    ds[i] = (row_ok && (c * 32 + i) < valid) ? v : 0.f;
+                    for (int i = 0; i < 32; ++i) {
+                        const float p = ex2_approx(fmaf(__uint_as_float(sr[i]), a.scale_log2, -lse2));
+                        ds[i] = p * (__uint_as_float(dpr[i]) - delta) * rscale;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float p = ex2_approx(fmaf(__uint_as_float(sr[i]), a.scale_log2, -lse2));
+                        const float v = p * (__uint_as_float(dpr[i]) - delta) * rscale;
+                        ds[i] = ((c * 32 + i) < valid) ? v : 0.f;
+                    }
                 }
                 store_row_chunk_sw128(ds_row, sw, c, ds);
             }
@@ -355,6 +364,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
         const uint32_t lane_off = uint32_t(warp * 32) << 16;
         const int kv = kv0 + row;
         const bool row_ok = kv < a.N;
+        const bool row_ok_warp = (kv0 + warp * 32 + 31) < a.N;  // every key row of this warp is valid
         uint8_t* pt_row = smem + DKV_SMEM_PT + row * 128;
         uint8_t* dst_row = smem + DKV_SMEM_DST + row * 128;
         const int sw = row & 7;
@@ -380,13 +390,22 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
                 tmem_ld_32x32b_x32(tmem_dpt + lane_off + c * 32, dpr);
                 tmem_ld_wait();
                 float p[32], ds[32];
+                if (row_ok_warp && c * 32 + 32 <= valid) {  // warp-uniform fast path
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const float l2 = st[c * 32 + q], dl = st[64 + c * 32 + q];
-                    const float pv = exp2f(fmaf(__uint_as_float(sr[q]), a.scale_log2, -l2));
-                    const bool ok = row_ok && (c * 32 + q) < valid;
-                    p[q] = ok ? pv : 0.f;
-                    ds[q] = ok ? a.scale * pv * (__uint_as_float(dpr[q]) - dl) : 0.f;
+                    for (int q = 0; q < 32; ++q) {
+                        const float l2 = st[c * 32 + q], dl = st[64 + c * 32 + q];
+                        p[q] = ex2_approx(fmaf(__uint_as_float(sr[q]), a.scale_log2, -l2));
+                        ds[q] = a.scale * p[q] * (__uint_as_float(dpr[q]) - dl);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const float l2 = st[c * 32 + q], dl = st[64 + c * 32 + q];
+                        const float pv = ex2_approx(fmaf(__uint_as_float(sr[q]), a.scale_log2, -l2));
+                        const bool ok = row_ok && (c * 32 + q) < valid;
+                        p[q] = ok ? pv : 0.f;
+                        ds[q] = ok ? a.scale * pv * (__uint_as_float(dpr[q]) - dl) : 0.f;
+                    }
                 }
                 store_row_chunk_sw128(pt_row, sw, c, p);
                 store_row_chunk_sw128(dst_row, sw, c, ds);

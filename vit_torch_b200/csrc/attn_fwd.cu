@@ -152,32 +152,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdArgs a) 
             const int nchunks = (valid + 31) >> 5;
             mbar_wait(s_full, j & 1);
             tc_fence_after_sync();
-            // pass 1: row max
+            // pass 1: row max (masking only in a partially valid chunk; the branch is warp-uniform)
             float mx = -INFINITY;
             for (int c = 0; c < nchunks; ++c) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_s + lane_off + c * 32, r);
                 tmem_ld_wait();
+                if (c * 32 + 32 <= valid) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float v = (c * 32 + i < valid) ? __uint_as_float(r[i]) : -INFINITY;
-                    mx = fmaxf(mx, v);
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        mx = fmaxf(mx, (c * 32 + i < valid) ? __uint_as_float(r[i]) : -INFINITY);
                 }
             }
             const float m_new = fmaxf(m_run, mx * a.scale_log2);
-            const float alpha = exp2f(m_run - m_new);
+            const float alpha = ex2_approx(m_run - m_new);
             float psum = 0.f;
-            // pass 2: p = exp2(s*scale_log2 - m_new) -> bf16 -> swizzled smem (A operand of the PV MMA)
+            // pass 2: p = exp2(s*scale_log2 - m_new) -> bf16 -> swizzled smem (A operand of the PV MMA). The loop is
+            // issue-bound: one FFMA + one MUFU.EX2 + one FADD per element, one cvt per pair.
             for (int c = 0; c < nchunks; ++c) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_s + lane_off + c * 32, r);
                 tmem_ld_wait();
                 float p[32];
+                if (c * 32 + 32 <= valid) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float v = exp2f(fmaf(__uint_as_float(r[i]), a.scale_log2, -m_new));
-                    p[i] = (c * 32 + i < valid) ? v : 0.f;
-                    psum += p[i];
+                    for (int i = 0; i < 32; ++i) {
+                        p[i] = ex2_approx(fmaf(__uint_as_float(r[i]), a.scale_log2, -m_new));
+                        psum += p[i];
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float v = ex2_approx(fmaf(__uint_as_float(r[i]), a.scale_log2, -m_new));
+                        p[i] = (c * 32 + i < valid) ? v : 0.f;
+                        psum += p[i];
+                    }
                 }
                 uint8_t* dst = p_row + (c >> 1) * AF_TILE_BYTES;
 #pragma unroll

@@ -69,6 +69,13 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
     return fmaf(x, pdf, cdf);
 }
 
+// single-instruction exp2 (MUFU.EX2): the softmax loops are issue-bound, exp2f() costs several instructions more
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
