@@ -9,7 +9,7 @@ import os
 from ctypes import c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvitk.so")
+LIB_PATH = os.environ.get("VITK_LIB") or os.path.join(_HERE, "libvitk.so")
 
 ERRORS = {
     -1: "VITK_ERR_ARG (bad shape / alignment / null pointer)",

@@ -149,6 +149,13 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
         "r"(c3), "r"(c4)
         : "memory");
 }
+// L2 prefetch of a tile (no smem destination, no barrier): turns the later TMA load of the same box into an L2 hit
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 // TMA store smem -> global (bulk group completion)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(

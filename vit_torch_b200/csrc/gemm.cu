@@ -2,6 +2,7 @@
 #include "gemm.cuh"
 #include "tmap.cuh"
 #include "../../include/vitk.h"
+#include <stdlib.h>
 
 namespace vitk {
 
@@ -128,12 +129,22 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
     int rc;
     // K-major operand: global [rows, K], box {64 k, rows};  MN-major operand: global [K, rows], box {64 rows, 64 k}
     const uint64_t nh = bt.nh, nb = bt.nb;
+    if (nh * nb == 1) {
+        g.a_perm[0] = g.b_perm[0] = 0; g.a_perm[1] = g.b_perm[1] = 1; g.a_perm[2] = g.b_perm[2] = 2;
+        if (!a_mn_major) rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM);
+        else             rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, GEMM_BK);
+        if (rc) return VITK_ERR_TMAP;
+        if (!b_mn_major) rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GEMM_BK, (uint32_t)BN);
+        else             rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BK);
+        if (rc) return VITK_ERR_TMAP;
+    } else {
     if (!a_mn_major) rc = make_tmap_4d_bf16(&tmA, g.a_perm, A, K, M, nh, nb, lda, bt.sa_h, bt.sa_b, GEMM_BK, GEMM_BM);
     else             rc = make_tmap_4d_bf16(&tmA, g.a_perm, A, M, K, nh, nb, lda, bt.sa_h, bt.sa_b, 64, GEMM_BK);
     if (rc) return VITK_ERR_TMAP;
     if (!b_mn_major) rc = make_tmap_4d_bf16(&tmB, g.b_perm, B, K, N, nh, nb, ldb, bt.sb_h, bt.sb_b, GEMM_BK, (uint32_t)BN);
     else             rc = make_tmap_4d_bf16(&tmB, g.b_perm, B, N, K, nh, nb, ldb, bt.sb_h, bt.sb_b, 64, GEMM_BK);
     if (rc) return VITK_ERR_TMAP;
+    }
 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (BN == 256) return dispatch_gemm<256>(a_mn_major != 0, b_mn_major != 0, epilogue, tmA, tmB, g, st);

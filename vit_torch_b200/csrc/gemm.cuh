@@ -181,6 +181,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     const int num_units = g.num_m_tiles * g.num_n_tiles * g.splits * g.nbatch_h * g.nbatch_b;
+    const bool batched = g.nbatch_h * g.nbatch_b > 1;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -201,8 +202,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 // operand coordinates: K-major tile = (k, row, bh, bb); MN-major tile = (row, k, bh, bb); the three
                 // outer coordinates are permuted into tensor-map dimension order
                 auto load_tile = [&](void* dst, const CUtensorMap* tm, const int* perm, int c0, int row) {
-                    const int lc[3] = {row, bh, bb};
-                    tma_load_4d(dst, tm, &full_bar[stage], c0, lc[perm[0]], lc[perm[1]], lc[perm[2]]);
+                    if (!batched) {   // plain GEMM: rank-2 tensor maps (cheaper for the TMA unit than rank-4 boxes)
+                        tma_load_2d(dst, tm, &full_bar[stage], c0, row);
+                    } else {
+                        const int lc[3] = {row, bh, bb};
+                        tma_load_4d(dst, tm, &full_bar[stage], c0, lc[perm[0]], lc[perm[1]], lc[perm[2]]);
+                    }
                 };
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
