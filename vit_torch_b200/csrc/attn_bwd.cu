@@ -9,7 +9,8 @@
 //                        Also produces delta (written to global for the second kernel).
 //   attn_bwd_dkv_kernel: CTA = (128 key rows,   head, batch), loops over 64-row Q/dO tiles; dK, dV accumulate in TMEM.
 // S and dP are recomputed in both (7 tile-GEMMs instead of 5) in exchange for no dQ atomics / conversion pass.
-// Inputs are read in place from the qkv Linear output [B,N,3,H,d] and dO [B,N,H,d] via 4-D TMA maps; gradients are
+// Inputs are read in place from the qkv Linear output [B,N,3,H,d] and dO [B,N,H,d] via rank-2 TMA maps (rows of a tile
+// past the image end belong to the next image and are masked; see make_tok_tmap2d); gradients are
 // written in place into dqkv [B,N,3,H,d] (the layout the qkv dgrad/wgrad GEMMs consume).
 #include "common.cuh"
 #include "tmap.cuh"
@@ -102,14 +103,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
     if (warp == 4) {
         if (lane == 0) {
             mbar_expect_tx(qdo_full, 2 * AB_T128);
-            tma_load_4d(smem + DQ_SMEM_Q, &tmQKV128, qdo_full, 0, h, q0, b);
-            tma_load_4d(smem + DQ_SMEM_DO, &tmDO128, qdo_full, 0, h, q0, b);
+            tma_load_2d(smem + DQ_SMEM_Q, &tmQKV128, qdo_full, h * HD, b * a.N + q0);
+            tma_load_2d(smem + DQ_SMEM_DO, &tmDO128, qdo_full, h * HD, b * a.N + q0);
             for (int j = 0; j < nkv; ++j) {
                 const int s = j & 1;
                 mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
                 mbar_expect_tx(&kv_full[s], 2 * AB_T64);
-                tma_load_4d(smem + DQ_SMEM_K + s * AB_T64, &tmQKV64, &kv_full[s], 0, a.H + h, j * 64, b);
-                tma_load_4d(smem + DQ_SMEM_V + s * AB_T64, &tmQKV64, &kv_full[s], 0, 2 * a.H + h, j * 64, b);
+                tma_load_2d(smem + DQ_SMEM_K + s * AB_T64, &tmQKV64, &kv_full[s], (a.H + h) * HD, b * a.N + j * 64);
+                tma_load_2d(smem + DQ_SMEM_V + s * AB_T64, &tmQKV64, &kv_full[s], (2 * a.H + h) * HD, b * a.N + j * 64);
             }
         }
     } else if (warp == 5) {
@@ -302,14 +303,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     if (warp == 4) {
         if (lane == 0) {
             mbar_expect_tx(kv_full, 2 * AB_T128);
-            tma_load_4d(smem + DKV_SMEM_K, &tmQKV128, kv_full, 0, a.H + h, kv0, b);
-            tma_load_4d(smem + DKV_SMEM_V, &tmQKV128, kv_full, 0, 2 * a.H + h, kv0, b);
+            tma_load_2d(smem + DKV_SMEM_K, &tmQKV128, kv_full, (a.H + h) * HD, b * a.N + kv0);
+            tma_load_2d(smem + DKV_SMEM_V, &tmQKV128, kv_full, (2 * a.H + h) * HD, b * a.N + kv0);
             for (int i = 0; i < nq; ++i) {
                 const int s = i & 1;
                 mbar_wait(&qdo_empty[s], ((i >> 1) & 1) ^ 1);
                 mbar_expect_tx(&qdo_full[s], 2 * AB_T64);
-                tma_load_4d(smem + DKV_SMEM_Q + s * AB_T64, &tmQKV64, &qdo_full[s], 0, h, i * 64, b);
-                tma_load_4d(smem + DKV_SMEM_DO + s * AB_T64, &tmDO64, &qdo_full[s], 0, h, i * 64, b);
+                tma_load_2d(smem + DKV_SMEM_Q + s * AB_T64, &tmQKV64, &qdo_full[s], h * HD, b * a.N + i * 64);
+                tma_load_2d(smem + DKV_SMEM_DO + s * AB_T64, &tmDO64, &qdo_full[s], h * HD, b * a.N + i * 64);
             }
         }
     } else if (warp == 5) {
@@ -447,14 +448,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     }
 }
 
-// 4-D map over a token-major bf16 tensor [B, N, G, d] (G = 3H for qkv, H for O/dO): dims {d, G, N, B}
-int make_tok_tmap(CUtensorMap* out, const void* p, int B, int N, int G, int d, int box_rows) {
-    const uint64_t pitch = (uint64_t)G * d;
-    uint64_t dims[4] = {(uint64_t)d, (uint64_t)G, (uint64_t)N, (uint64_t)B};
-    uint64_t strides[3] = {(uint64_t)d * 2, pitch * 2, (uint64_t)N * pitch * 2};
-    uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
-    return make_tmap(out, p, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
-}
+int make_tok_tmap2d(CUtensorMap* out, const void* p, long long rows, long long cols, int box_rows);  // attn_fwd.cu
 
 template <int HD>
 static int launch_attn_bwd(const CUtensorMap& q128, const CUtensorMap& q64, const CUtensorMap& do128,
@@ -482,8 +476,10 @@ extern "C" int vitk_attn_bwd(const void* qkv_bf16, const void* out_bf16, const v
     if (B <= 0 || N <= 0 || H <= 0 || !(d == 64 || d == 48)) return VITK_ERR_ARG;
     if (!qkv_bf16 || !out_bf16 || !dout_bf16 || !lse2 || !delta || !dqkv_bf16) return VITK_ERR_ARG;
     CUtensorMap q128, q64, do128, do64;
-    if (make_tok_tmap(&q128, qkv_bf16, B, N, 3 * H, d, 128) || make_tok_tmap(&q64, qkv_bf16, B, N, 3 * H, d, 64) ||
-        make_tok_tmap(&do128, dout_bf16, B, N, H, d, 128) || make_tok_tmap(&do64, dout_bf16, B, N, H, d, 64))
+    const long long rows = (long long)B * N;
+    if (make_tok_tmap2d(&q128, qkv_bf16, rows, 3LL * H * d, 128) || make_tok_tmap2d(&q64, qkv_bf16, rows, 3LL * H * d, 64) ||
+        make_tok_tmap2d(&do128, dout_bf16, rows, (long long)H * d, 128) ||
+        make_tok_tmap2d(&do64, dout_bf16, rows, (long long)H * d, 64))
         return VITK_ERR_TMAP;
     AttnBwdArgs a;
     a.B = B; a.H = H; a.N = N; a.D = H * d;

@@ -4,8 +4,8 @@
 // models/swin.py:119-144): attn = (q @ k^T) * scale; softmax; attn @ v -- without materialising [B,H,N,N].
 //
 // Layout: qkv is the raw output of the qkv Linear, bf16 [B, N, 3, H, d] (= rows [B*N, 3*H*d]); Q/K/V tiles are
-// fetched straight out of it with one 4-D TMA map {d, 3H, N, B} (box {64, 1, 128, 1}, 128B swizzle; rows >= N and
-// columns >= d are zero-filled by TMA). O is written bf16 [B, N, H, d] (heads merged = the layout proj consumes),
+// fetched straight out of it with one 2-D TMA map over [B*N, 3*H*d] (box {64, 128}, 128B swizzle; rows >= N of a tile
+// belong to the next image and are masked, rows past the tensor end are zero-filled by TMA). O is written bf16 [B, N, H, d] (heads merged = the layout proj consumes),
 // lse2[b,h,n] = log2-domain logsumexp of the scaled scores (saved for backward).
 //
 // One CTA = one (q-block of 128 rows, head, batch). Warps 0-3: softmax (thread == query row, TMEM lane == row),
@@ -85,14 +85,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdArgs a) 
         // ===================== TMA producer =====================
         if (lane == 0) {
             mbar_expect_tx(q_full, AF_TILE_BYTES);
-            tma_load_4d(smem + AF_SMEM_Q, &tmQKV, q_full, 0, h, q0, b);
+            tma_load_2d(smem + AF_SMEM_Q, &tmQKV, q_full, h * HD, b * a.N + q0);
             for (int j = 0; j < nkv; ++j) {
                 const int s = j & 1;
                 mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
                 mbar_expect_tx(&k_full[s], AF_TILE_BYTES);
-                tma_load_4d(smem + AF_SMEM_K + s * AF_TILE_BYTES, &tmQKV, &k_full[s], 0, a.H + h, j * AF_BKV, b);
+                tma_load_2d(smem + AF_SMEM_K + s * AF_TILE_BYTES, &tmQKV, &k_full[s], (a.H + h) * HD, b * a.N + j * AF_BKV);
                 mbar_expect_tx(&v_full[s], AF_TILE_BYTES);
-                tma_load_4d(smem + AF_SMEM_V + s * AF_TILE_BYTES, &tmQKV, &v_full[s], 0, 2 * a.H + h, j * AF_BKV, b);
+                tma_load_2d(smem + AF_SMEM_V + s * AF_TILE_BYTES, &tmQKV, &v_full[s], (2 * a.H + h) * HD, b * a.N + j * AF_BKV);
             }
         }
     } else if (warp == 5) {
@@ -244,12 +244,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdArgs a) 
     }
 }
 
-// 4-D map over qkv bf16 [B, N, 3H, d]: dims {d, 3H, N, B}
-int make_qkv_tmap(CUtensorMap* out, const void* qkv, int B, int N, int H, int d, long long row_pitch_elems) {
-    uint64_t dims[4] = {(uint64_t)d, (uint64_t)(3 * H), (uint64_t)N, (uint64_t)B};
-    uint64_t strides[3] = {(uint64_t)d * 2, (uint64_t)row_pitch_elems * 2, (uint64_t)N * row_pitch_elems * 2};
-    uint32_t box[4] = {64, 1, 128, 1};
-    return make_tmap(out, qkv, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+// 2-D map over a token-major bf16 tensor viewed as [B*N rows, G*d columns] (G = 3H for qkv, H for O / dO), box
+// {64 columns, box_rows}. Rank-2 boxes are markedly cheaper for the TMA unit than the rank-4 {d, G, N, B} form; the
+// price is that a tile may run past its image into the next one (rows) or the next head (columns, d = 48): every
+// consumer masks those rows / columns (softmax columns >= N, k-steps and UMMA N limited to d), and rows past the end
+// of the tensor are zero-filled by TMA.
+int make_tok_tmap2d(CUtensorMap* out, const void* p, long long rows, long long cols, int box_rows) {
+    return make_tmap_2d_bf16(out, p, (uint64_t)cols, (uint64_t)rows, (uint64_t)cols, 64, (uint32_t)box_rows);
 }
 
 }  // namespace vitk
@@ -260,7 +261,7 @@ extern "C" int vitk_attn_fwd(const void* qkv_bf16, void* out_bf16, float* lse2, 
                              float scale, void* stream) {
     if (B <= 0 || N <= 0 || H <= 0 || !(d == 64 || d == 48) || !qkv_bf16 || !out_bf16 || !lse2) return VITK_ERR_ARG;
     CUtensorMap tm;
-    if (make_qkv_tmap(&tm, qkv_bf16, B, N, H, d, 3LL * H * d)) return VITK_ERR_TMAP;
+    if (make_tok_tmap2d(&tm, qkv_bf16, (long long)B * N, 3LL * H * d, 128)) return VITK_ERR_TMAP;
     AttnFwdArgs a;
     a.B = B; a.H = H; a.N = N; a.D = H * d;
     a.scale_log2 = scale * 1.4426950408889634f;
