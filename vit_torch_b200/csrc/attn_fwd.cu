@@ -4,14 +4,22 @@
 // models/swin.py:119-144): attn = (q @ k^T) * scale; softmax; attn @ v -- without materialising [B,H,N,N].
 //
 // Layout: qkv is the raw output of the qkv Linear, bf16 [B, N, 3, H, d] (= rows [B*N, 3*H*d]); Q/K/V tiles are
-// fetched straight out of it with one 2-D TMA map over [B*N, 3*H*d] (box {64, 128}, 128B swizzle; rows >= N of a tile
-// belong to the next image and are masked, rows past the tensor end are zero-filled by TMA). O is written bf16 [B, N, H, d] (heads merged = the layout proj consumes),
-// lse2[b,h,n] = log2-domain logsumexp of the scaled scores (saved for backward).
+// fetched straight out of it with 2-D TMA maps over [B*N, 3*H*d] (128B swizzle; rows >= N of a tile belong to the next
+// image and are masked, rows past the tensor end are zero-filled by TMA). O is written bf16 [B, N, H, d] (heads
+// merged = the layout proj consumes), lse2[b,h,n] = log2-domain logsumexp of the scaled scores (saved for backward).
 //
 // One CTA = one (q-block of 128 rows, head, batch). Warps 0-3: softmax (thread == query row, TMEM lane == row),
-// warp 4: TMA producer, warp 5: MMA issuer + TMEM allocator. S = Q K_j^T lives in TMEM (128 fp32 columns); P_j is
-// written as bf16 into a 128B-swizzled K-major smem tile and multiplied with V_j (MN-major B operand) into a 64-column
-// TMEM scratch; the running O is rescaled and accumulated in registers (online softmax).
+// warp 4: TMA producer, warp 5: MMA issuer + TMEM allocator. Key/value tiles are 64 rows.
+//
+// The kernel is bound by TMEM read bandwidth (64 B/clk/SM) and instruction issue, not by the tensor pipe, so every
+// score is read from TMEM exactly ONCE and the output accumulator never leaves TMEM:
+//   * S_j = Q K_j^T (UMMA 128 x 64 x 16 into 64 TMEM columns) is loaded into registers in one go, which frees the S
+//     columns for the next tile immediately;
+//   * exponentials use a per-row reference maximum m_ref that is only raised (and O / l rescaled, through
+//     tcgen05.ld/st) when a row maximum exceeds it by more than 2^8 (lazy rescaling: p <= 256 keeps fp32/bf16 exact
+//     enough, lse2 = m_ref + log2(l) stays exact);
+//   * P_j (bf16, 128B-swizzled K-major smem tile, double-buffered) x V_j (MN-major B operand read from the token-major
+//     tile) accumulates straight into the 64 O columns of TMEM; O is read once at the end.
 #include "common.cuh"
 #include "tmap.cuh"
 #include "../../include/vitk.h"
@@ -19,16 +27,18 @@
 namespace vitk {
 
 constexpr int AF_BQ = 128;
-constexpr int AF_BKV = 128;
+constexpr int AF_BKV = 64;
 constexpr int AF_THREADS = 192;
-constexpr int AF_TILE_BYTES = 128 * 128;                    // one [128 rows x 64 bf16] swizzled tile
+constexpr int AF_QTILE = 128 * 128;                       // [128 rows x 64 bf16] swizzled tile
+constexpr int AF_KVTILE = AF_BKV * 128;                   // [64 rows x 64 bf16]
 constexpr int AF_SMEM_Q = 0;
-constexpr int AF_SMEM_K = AF_SMEM_Q + AF_TILE_BYTES;        // 2 stages
-constexpr int AF_SMEM_V = AF_SMEM_K + 2 * AF_TILE_BYTES;    // 2 stages
-constexpr int AF_SMEM_P = AF_SMEM_V + 2 * AF_TILE_BYTES;    // 2 k-chunks of 64 columns
-constexpr int AF_SMEM_BAR = AF_SMEM_P + 2 * AF_TILE_BYTES;  // 114688
+constexpr int AF_SMEM_K = AF_SMEM_Q + AF_QTILE;           // 2 stages
+constexpr int AF_SMEM_V = AF_SMEM_K + 2 * AF_KVTILE;      // 2 stages
+constexpr int AF_SMEM_P = AF_SMEM_V + 2 * AF_KVTILE;      // 2 buffers [128 x 64] bf16
+constexpr int AF_SMEM_BAR = AF_SMEM_P + 2 * AF_QTILE;     // 81920
 constexpr int AF_SMEM_BYTES = AF_SMEM_BAR + 256;
-constexpr uint32_t AF_TMEM_COLS = 256;                      // S: [0,128)  O scratch: [128,192)
+constexpr uint32_t AF_TMEM_COLS = 128;                    // S: [0,64)  O: [64,128)
+constexpr float AF_RESCALE_TAU = 8.0f;                    // log2 units
 
 struct AttnFwdArgs {
     int B, H, N, D;  // D = H * d
@@ -39,7 +49,8 @@ struct AttnFwdArgs {
 
 template <int HD>
 __global__ void __launch_bounds__(AF_THREADS, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdArgs a) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                const AttnFwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AF_SMEM_BAR);
     uint64_t* q_full = bars + 0;
@@ -48,10 +59,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdArgs a) 
     uint64_t* kv_empty = bars + 5;  // [2]
     uint64_t* s_full = bars + 7;
     uint64_t* s_free = bars + 8;
-    uint64_t* p_full = bars + 9;
-    uint64_t* o_full = bars + 10;
-    uint64_t* o_free = bars + 11;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* p_full = bars + 9;    // [2]
+    uint64_t* o_full = bars + 11;   // [2]  PV_j complete (j even / odd)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qblk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -60,39 +70,47 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdArgs a) 
 
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need 1 KB alignment
     if (warp == 4 && lane == 0) {
-        tma_prefetch_desc(&tmQKV);
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmKV);
         mbar_init(q_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&k_full[i], 1);
             mbar_init(&v_full[i], 1);
             mbar_init(&kv_empty[i], 1);
+            mbar_init(&p_full[i], 128);
+            mbar_init(&o_full[i], 1);
         }
         mbar_init(s_full, 1);
         mbar_init(s_free, 128);
-        mbar_init(p_full, 128);
-        mbar_init(o_full, 1);
-        mbar_init(o_free, 128);
         fence_mbar_init();
+        // first loads go out before the block-wide sync: their latency overlaps the TMEM allocation
+        mbar_expect_tx(q_full, AF_QTILE);
+        tma_load_2d(smem + AF_SMEM_Q, &tmQ, q_full, h * HD, b * a.N + q0);
+        for (int j = 0; j < 2 && j < nkv; ++j) {
+            mbar_expect_tx(&k_full[j], AF_KVTILE);
+            tma_load_2d(smem + AF_SMEM_K + j * AF_KVTILE, &tmKV, &k_full[j], (a.H + h) * HD, b * a.N + j * AF_BKV);
+            mbar_expect_tx(&v_full[j], AF_KVTILE);
+            tma_load_2d(smem + AF_SMEM_V + j * AF_KVTILE, &tmKV, &v_full[j], (2 * a.H + h) * HD, b * a.N + j * AF_BKV);
+        }
     }
     if (warp == 5) tmem_alloc<AF_TMEM_COLS>(tmem_slot);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+    const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + AF_BKV;
 
     if (warp == 4) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_expect_tx(q_full, AF_TILE_BYTES);
-            tma_load_2d(smem + AF_SMEM_Q, &tmQKV, q_full, h * HD, b * a.N + q0);
-            for (int j = 0; j < nkv; ++j) {
+            for (int j = 2; j < nkv; ++j) {   // tiles 0 and 1 were issued in the prologue
                 const int s = j & 1;
                 mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-                mbar_expect_tx(&k_full[s], AF_TILE_BYTES);
-                tma_load_2d(smem + AF_SMEM_K + s * AF_TILE_BYTES, &tmQKV, &k_full[s], (a.H + h) * HD, b * a.N + j * AF_BKV);
-                mbar_expect_tx(&v_full[s], AF_TILE_BYTES);
-                tma_load_2d(smem + AF_SMEM_V + s * AF_TILE_BYTES, &tmQKV, &v_full[s], (2 * a.H + h) * HD, b * a.N + j * AF_BKV);
+                mbar_expect_tx(&k_full[s], AF_KVTILE);
+                tma_load_2d(smem + AF_SMEM_K + s * AF_KVTILE, &tmKV, &k_full[s], (a.H + h) * HD, b * a.N + j * AF_BKV);
+                mbar_expect_tx(&v_full[s], AF_KVTILE);
+                tma_load_2d(smem + AF_SMEM_V + s * AF_KVTILE, &tmKV, &v_full[s], (2 * a.H + h) * HD,
+                            b * a.N + j * AF_BKV);
             }
         }
     } else if (warp == 5) {
@@ -108,7 +126,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdArgs a) 
                 tc_fence_after_sync();
                 const uint32_t idesc = make_idesc_bf16(128, ncols, 0, 0);
                 const uint64_t adesc = make_smem_desc_sw128(q_addr, 0, 1024);
-                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + AF_SMEM_K + s * AF_TILE_BYTES), 0, 1024);
+                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + AF_SMEM_K + s * AF_KVTILE), 0, 1024);
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_s, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
                 umma_commit(s_full);
@@ -120,120 +138,132 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdArgs a) 
                 if (j + 1 < nkv) issue_s(j + 1);
                 const int valid = min(AF_BKV, a.N - j * AF_BKV);
                 const int ksteps = (valid + 15) >> 4;
-                mbar_wait(p_full, j & 1);
+                mbar_wait(&p_full[s], (j >> 1) & 1);
                 mbar_wait(&v_full[s], (j >> 1) & 1);
-                if (j > 0) mbar_wait(o_free, (j - 1) & 1);
                 tc_fence_after_sync();
-                // O_scratch[128, HD] = P[128, kv] * V[kv, HD]: A = P (K-major), B = V tile read MN-major
+                // O[128, HD] += P_j[128, kv] * V_j[kv, HD]: A = P (K-major), B = V tile read MN-major
                 constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, 0, 1);
-                const uint32_t v_addr = smem_u32(smem + AF_SMEM_V + s * AF_TILE_BYTES);
+                const uint32_t v_addr = smem_u32(smem + AF_SMEM_V + s * AF_KVTILE);
                 for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t adesc = make_smem_desc_sw128(p_addr + (k >> 2) * AF_TILE_BYTES + (k & 3) * 32, 0, 1024);
+                    const uint64_t adesc = make_smem_desc_sw128(p_addr + s * AF_QTILE + k * 32, 0, 1024);
                     const uint64_t bdesc = make_smem_desc_sw128(v_addr + k * 2048, AF_BKV * 128, 1024);
-                    umma_bf16(tmem_o, adesc, bdesc, idesc_pv, k > 0);
+                    umma_bf16(tmem_o, adesc, bdesc, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
                 }
-                umma_commit(o_full);
+                umma_commit(&o_full[s]);
                 umma_commit(&kv_empty[s]);
             }
         }
     } else {
-        // ===================== softmax / accumulate (thread == query row) =====================
+        // ===================== softmax (thread == query row) =====================
         const int row = warp * 32 + lane;
         const uint32_t lane_off = uint32_t(warp * 32) << 16;
-        float m_run = -INFINITY, l_run = 0.f;
-        float o_acc[HD];
-#pragma unroll
-        for (int i = 0; i < HD; ++i) o_acc[i] = 0.f;
-        uint8_t* p_row = smem + AF_SMEM_P + row * 128;
+        float m_ref = -INFINITY, l_run = 0.f;
         const int sw = row & 7;
 
         for (int j = 0; j < nkv; ++j) {
             const int valid = min(AF_BKV, a.N - j * AF_BKV);
-            const int nchunks = (valid + 31) >> 5;
             mbar_wait(s_full, j & 1);
             tc_fence_after_sync();
-            // pass 1: row max (masking only in a partially valid chunk; the branch is warp-uniform)
-            float mx = -INFINITY;
-            for (int c = 0; c < nchunks; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem_s + lane_off + c * 32, r);
-                tmem_ld_wait();
-                if (c * 32 + 32 <= valid) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        mx = fmaxf(mx, (c * 32 + i < valid) ? __uint_as_float(r[i]) : -INFINITY);
-                }
-            }
-            const float m_new = fmaxf(m_run, mx * a.scale_log2);
-            const float alpha = ex2_approx(m_run - m_new);
-            float psum = 0.f;
-            // pass 2: p = exp2(s*scale_log2 - m_new) -> bf16 -> swizzled smem (A operand of the PV MMA). The loop is
-            // issue-bound: one FFMA + one MUFU.EX2 + one FADD per element, one cvt per pair.
-            for (int c = 0; c < nchunks; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem_s + lane_off + c * 32, r);
-                tmem_ld_wait();
-                float p[32];
-                if (c * 32 + 32 <= valid) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        p[i] = ex2_approx(fmaf(__uint_as_float(r[i]), a.scale_log2, -m_new));
-                        psum += p[i];
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float v = ex2_approx(fmaf(__uint_as_float(r[i]), a.scale_log2, -m_new));
-                        p[i] = (c * 32 + i < valid) ? v : 0.f;
-                        psum += p[i];
-                    }
-                }
-                uint8_t* dst = p_row + (c >> 1) * AF_TILE_BYTES;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint4 pk = make_uint4(pack_bf16(p[u * 8 + 0], p[u * 8 + 1]), pack_bf16(p[u * 8 + 2], p[u * 8 + 3]),
-                                                pack_bf16(p[u * 8 + 4], p[u * 8 + 5]), pack_bf16(p[u * 8 + 6], p[u * 8 + 7]));
-                    const int unit = (c & 1) * 4 + u;
-                    *reinterpret_cast<uint4*>(dst + ((unit ^ sw) << 4)) = pk;
-                }
-            }
+            // the whole score tile goes to registers in one TMEM pass; the S columns are free again right away
+            uint32_t sr[AF_BKV];
+            tmem_ld_32x32b_x32(tmem_s + lane_off, sr);
+            if (valid > 32) tmem_ld_32x32b_x32(tmem_s + lane_off + 32, sr + 32);
+            tmem_ld_wait();
             tc_fence_before_sync();
             mbar_arrive(s_free);
+            // four independent chains: with one or two warps per scheduler a 64-deep dependent FMNMX / FADD chain is
+            // pure latency
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            if (valid == AF_BKV) {
+#pragma unroll
+                for (int i = 0; i < AF_BKV; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sr[i]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < AF_BKV; ++i)
+                    mx4[i & 3] = fmaxf(mx4[i & 3], (i < valid) ? __uint_as_float(sr[i]) : -INFINITY);
+            }
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            const float mxs = mx * a.scale_log2;
+            if (j == 0) {
+                m_ref = mxs;
+            } else if (__any_sync(0xffffffffu, mxs > m_ref + AF_RESCALE_TAU)) {
+                // lazy rescale (warp-uniform branch): raise the reference maximum and rescale l and the TMEM accumulator
+                mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);   // PV_{j-1} has landed in O
+                tc_fence_after_sync();
+                const float m_new = fmaxf(m_ref, mxs);
+                const float alpha = ex2_approx(m_ref - m_new);
+                l_run *= alpha;
+                m_ref = m_new;
+#pragma unroll
+                for (int c = 0; c < HD / 16; ++c) {
+                    uint32_t r[16];
+                    tmem_ld_32x32b_x16(tmem_o + lane_off + c * 16, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                    tmem_st_32x32b_x16(tmem_o + lane_off + c * 16, r);
+                }
+                tmem_st_wait();
+                tc_fence_before_sync();
+            }
+            // P buffer (j & 1) was last read by PV_{j-2}
+            if (j >= 2) mbar_wait(&o_full[j & 1], ((j - 2) >> 1) & 1);
+            uint8_t* p_row = smem + AF_SMEM_P + (j & 1) * AF_QTILE + row * 128;
+            float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+            const float nm = -m_ref;
+            if (valid == AF_BKV) {
+#pragma unroll
+                for (int u = 0; u < AF_BKV / 8; ++u) {
+                    float p[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        p[i] = ex2_approx(fmaf(__uint_as_float(sr[u * 8 + i]), a.scale_log2, nm));
+                        ps4[i & 3] += p[i];
+                    }
+                    *reinterpret_cast<uint4*>(p_row + ((u ^ sw) << 4)) = make_uint4(
+                        pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < AF_BKV / 8; ++u) {
+                    if (u < ((valid + 15) >> 4) * 2) {   // 16-byte units of 8 columns that the PV MMA may read
+                        float p[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float v = ex2_approx(fmaf(__uint_as_float(sr[u * 8 + i]), a.scale_log2, nm));
+                            p[i] = (u * 8 + i < valid) ? v : 0.f;
+                            ps4[i & 3] += p[i];
+                        }
+                        *reinterpret_cast<uint4*>(p_row + ((u ^ sw) << 4)) = make_uint4(
+                            pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+                    }
+                }
+            }
+            const float psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+            l_run += psum;
             fence_proxy_async_smem();
-            mbar_arrive(p_full);
-            l_run = l_run * alpha + psum;
-            m_run = m_new;
-            // accumulate O
-            mbar_wait(o_full, j & 1);
-            tc_fence_after_sync();
-#pragma unroll
-            for (int c = 0; c < HD / 16; ++c) {
-                uint32_t r[16];
-                tmem_ld_32x32b_x16(tmem_o + lane_off + c * 16, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] = fmaf(o_acc[c * 16 + i], alpha, __uint_as_float(r[i]));
-            }
-            tc_fence_before_sync();
-            mbar_arrive(o_free);
+            mbar_arrive(&p_full[j & 1]);
         }
+        // epilogue: the accumulator is read from TMEM exactly once
+        mbar_wait(&o_full[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
+        tc_fence_after_sync();
         const int n = q0 + row;
-        if (n < a.N) {
-            const float inv = 1.0f / l_run;
-            __nv_bfloat16* dst = a.out + ((long long)b * a.N + n) * a.D + h * HD;
+        const float inv = 1.0f / l_run;
+        __nv_bfloat16* dst = a.out + ((long long)b * a.N + n) * a.D + h * HD;
+        uint32_t r[HD];
 #pragma unroll
-            for (int u = 0; u < HD / 8; ++u) {
-                const uint4 pk = make_uint4(pack_bf16(o_acc[u * 8 + 0] * inv, o_acc[u * 8 + 1] * inv),
-                                            pack_bf16(o_acc[u * 8 + 2] * inv, o_acc[u * 8 + 3] * inv),
-                                            pack_bf16(o_acc[u * 8 + 4] * inv, o_acc[u * 8 + 5] * inv),
-                                            pack_bf16(o_acc[u * 8 + 6] * inv, o_acc[u * 8 + 7] * inv));
-                st_v4(dst + u * 8, pk);
-            }
-            a.lse2[((long long)b * a.H + h) * a.N + n] = m_run + log2f(l_run);
+        for (int c = 0; c < HD / 16; ++c) tmem_ld_32x32b_x16(tmem_o + lane_off + c * 16, r + c * 16);  // warp-collective
+        tmem_ld_wait();
+        if (n < a.N) {
+            const float* f = reinterpret_cast<const float*>(r);
+#pragma unroll
+            for (int u = 0; u < HD / 8; ++u)
+                st_v4(dst + u * 8, make_uint4(pack_bf16(f[u * 8 + 0] * inv, f[u * 8 + 1] * inv),
+                                              pack_bf16(f[u * 8 + 2] * inv, f[u * 8 + 3] * inv),
+                                              pack_bf16(f[u * 8 + 4] * inv, f[u * 8 + 5] * inv),
+                                              pack_bf16(f[u * 8 + 6] * inv, f[u * 8 + 7] * inv)));
         }
+        if (n < a.N) a.lse2[((long long)b * a.H + h) * a.N + n] = m_ref + log2f(l_run);
     }
 
     tc_fence_before_sync();
@@ -253,6 +283,24 @@ int make_tok_tmap2d(CUtensorMap* out, const void* p, long long rows, long long c
     return make_tmap_2d_bf16(out, p, (uint64_t)cols, (uint64_t)rows, (uint64_t)cols, 64, (uint32_t)box_rows);
 }
 
+template <int HD>
+static int launch_attn_fwd(const void* qkv, const AttnFwdArgs& a, int B, int N, int H, int d, cudaStream_t st) {
+    CUtensorMap tmq, tmkv;
+    if (make_tok_tmap2d(&tmq, qkv, (long long)B * N, 3LL * H * d, 128) ||
+        make_tok_tmap2d(&tmkv, qkv, (long long)B * N, 3LL * H * d, AF_BKV))
+        return VITK_ERR_TMAP;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_BYTES) !=
+            cudaSuccess)
+            return VITK_ERR_CUDA;
+        attr = true;
+    }
+    dim3 grid((N + AF_BQ - 1) / AF_BQ, H, B);
+    attn_fwd_kernel<HD><<<grid, AF_THREADS, AF_SMEM_BYTES, st>>>(tmq, tmkv, a);
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
 }  // namespace vitk
 
 using namespace vitk;
@@ -260,30 +308,12 @@ using namespace vitk;
 extern "C" int vitk_attn_fwd(const void* qkv_bf16, void* out_bf16, float* lse2, int B, int N, int H, int d,
                              float scale, void* stream) {
     if (B <= 0 || N <= 0 || H <= 0 || !(d == 64 || d == 48) || !qkv_bf16 || !out_bf16 || !lse2) return VITK_ERR_ARG;
-    CUtensorMap tm;
-    if (make_tok_tmap2d(&tm, qkv_bf16, (long long)B * N, 3LL * H * d, 128)) return VITK_ERR_TMAP;
     AttnFwdArgs a;
     a.B = B; a.H = H; a.N = N; a.D = H * d;
     a.scale_log2 = scale * 1.4426950408889634f;
     a.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
     a.lse2 = lse2;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    dim3 grid((N + AF_BQ - 1) / AF_BQ, H, B);
-    static bool attr64 = false, attr48 = false;
-    if (d == 64) {
-        if (!attr64) {
-            if (cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_BYTES) != cudaSuccess)
-                return VITK_ERR_CUDA;
-            attr64 = true;
-        }
-        attn_fwd_kernel<64><<<grid, AF_THREADS, AF_SMEM_BYTES, st>>>(tm, a);
-    } else {
-        if (!attr48) {
-            if (cudaFuncSetAttribute(attn_fwd_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_BYTES) != cudaSuccess)
-                return VITK_ERR_CUDA;
-            attr48 = true;
-        }
-        attn_fwd_kernel<48><<<grid, AF_THREADS, AF_SMEM_BYTES, st>>>(tm, a);
-    }
-    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+    if (d == 64) return launch_attn_fwd<64>(qkv_bf16, a, B, N, H, d, st);
+    return launch_attn_fwd<48>(qkv_bf16, a, B, N, H, d, st);
 }

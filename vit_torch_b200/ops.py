@@ -331,3 +331,50 @@ def class_attn_bwd(q, kc, kx, vc, vx, ldkv, ldc, p, dout, scale, dq, dkc, dkx, d
                                   ptr(dq), ptr(dkc), ptr(dkx), ptr(dvc), ptr(dvx), lddkv, lddc, B, H, n, d, _stream()),
           "vitk_class_attn_bwd")
     launch_count += 1
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# optional per-op CUDA-event timing of every wrapper in this module (scripts/step_breakdown.py)
+# ------------------------------------------------------------------------------------------------------------------
+_op_events = None
+
+
+def op_timing_begin():
+    global _op_events
+    _op_events = []
+
+
+def op_timing_end():
+    """Returns {op name: (total ms, launches)} since op_timing_begin()."""
+    global _op_events
+    ev, _op_events = _op_events, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, s, e in ev:
+        t, n = out.get(name, (0.0, 0))
+        out[name] = (t + s.elapsed_time(e), n + 1)
+    return out
+
+
+def _timed(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        if _op_events is None:
+            return fn(*a, **k)
+        s = torch.cuda.Event(enable_timing=True)
+        e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = fn(*a, **k)
+        e.record()
+        _op_events.append((fn.__name__, s, e))
+        return r
+
+    return wrapper
+
+
+for _name in ("gemm", "gemm_batched", "layernorm_fwd", "layernorm_bwd", "layernorm_fwd_rows", "layernorm_bwd_rows",
+              "colsum_accum", "colsum_f32_accum", "colsum_prod_accum", "cast_bf16", "attn_fwd", "attn_bwd", "scale_cast",
+              "patchify", "prefix_tokens", "th_mix_fwd", "th_mix_bwd", "class_attn_fwd", "class_attn_bwd"):
+    globals()[_name] = _timed(globals()[_name])
