@@ -199,37 +199,59 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int m0 = m_tile * GEMM_BM, n0 = n_tile * BN;
                 const int kb0 = split * g.kblocks_per_split;
                 const int kb1 = min(kb0 + g.kblocks_per_split, g.num_kblocks);
-                // operand coordinates: K-major tile = (k, row, bh, bb); MN-major tile = (row, k, bh, bb); the three
-                // outer coordinates are permuted into tensor-map dimension order
-                auto load_tile = [&](void* dst, const CUtensorMap* tm, const int* perm, int c0, int row) {
-                    if (!batched) {   // plain GEMM: rank-2 tensor maps (cheaper for the TMA unit than rank-4 boxes)
-                        tma_load_2d(dst, tm, &full_bar[stage], c0, row);
-                    } else {
+                if (!batched) {
+                    // plain GEMM: rank-2 tensor maps (rank-4 boxes cost 20-45% on MN-major operands)
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                        uint8_t* sa = smem_a + stage * Cfg::A_STAGE_BYTES;
+                        uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
+                        const int k0 = kb * GEMM_BK;
+                        if constexpr (!A_MN) {
+                            tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);  // box {64 k, 128 m}
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < GEMM_BM / 64; ++j)  // box {64 m, 64 k} per 64-wide M chunk
+                                tma_load_2d(sa + j * (GEMM_BK * 128), &tmA, &full_bar[stage], m0 + 64 * j, k0);
+                        }
+                        if constexpr (!B_MN) {
+                            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);  // box {64 k, BN n}
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j)
+                                tma_load_2d(sb + j * (GEMM_BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, k0);
+                        }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                } else {
+                    // batched: rank-4 maps {inner, row, batch_h, batch_b}; the three outer coordinates are permuted into
+                    // tensor-map dimension order (dims are sorted by stride on the host)
+                    auto load_tile = [&](void* dst, const CUtensorMap* tm, const int* perm, int c0, int row) {
                         const int lc[3] = {row, bh, bb};
                         tma_load_4d(dst, tm, &full_bar[stage], c0, lc[perm[0]], lc[perm[1]], lc[perm[2]]);
-                    }
-                };
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    uint8_t* sa = smem_a + stage * Cfg::A_STAGE_BYTES;
-                    uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
-                    const int k0 = kb * GEMM_BK;
-                    if constexpr (!A_MN) {
-                        load_tile(sa, &tmA, g.a_perm, k0, m0);  // box {64 k, 128 m}
-                    } else {
+                    };
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                        uint8_t* sa = smem_a + stage * Cfg::A_STAGE_BYTES;
+                        uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
+                        const int k0 = kb * GEMM_BK;
+                        if constexpr (!A_MN) {
+                            load_tile(sa, &tmA, g.a_perm, k0, m0);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < GEMM_BM / 64; ++j)  // box {64 m, 64 k} per 64-wide M chunk
-                            load_tile(sa + j * (GEMM_BK * 128), &tmA, g.a_perm, m0 + 64 * j, k0);
-                    }
-                    if constexpr (!B_MN) {
-                        load_tile(sb, &tmB, g.b_perm, k0, n0);  // box {64 k, BN n}
-                    } else {
+                            for (int j = 0; j < GEMM_BM / 64; ++j)
+                                load_tile(sa + j * (GEMM_BK * 128), &tmA, g.a_perm, m0 + 64 * j, k0);
+                        }
+                        if constexpr (!B_MN) {
+                            load_tile(sb, &tmB, g.b_perm, k0, n0);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j)
-                            load_tile(sb + j * (GEMM_BK * 128), &tmB, g.b_perm, n0 + 64 * j, k0);
+                            for (int j = 0; j < BN / 64; ++j)
+                                load_tile(sb + j * (GEMM_BK * 128), &tmB, g.b_perm, n0 + 64 * j, k0);
+                        }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -287,24 +309,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int m_tile = mb % g.num_m_tiles;
             const int batch = mb / g.num_m_tiles;
             const long long ooff = (long long)(batch % g.nbatch_h) * g.so_h + (long long)(batch / g.nbatch_h) * g.so_b;
-            float* sb = svec + as * 2 * BN;  // buffer index follows the accumulator stage (alternates per tile)
-            float* sg = sb + BN;
-            const bool use_vec = kUsesVec && (g.bias != nullptr || g.gamma != nullptr);
-            if (use_vec) {
-                // stage bias / gamma of this N tile in shared memory while the mainloop is still running
-                if (et < BN) {
-                    const int cidx = n_tile * BN + et;
-                    sts_f1(smem_u32(sb + et), (g.bias != nullptr && cidx < g.N) ? __ldg(g.bias + cidx) : 0.f);
-                    sts_f1(smem_u32(sg + et), (g.gamma != nullptr && cidx < g.N) ? __ldg(g.gamma + cidx) : 1.f);
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-            }
+            const bool has_bias = kUsesVec && g.bias != nullptr;
+            const bool has_gamma = (EPI == EPI_RESID_F32) && g.gamma != nullptr;
             // coalesced-domain coordinates of this lane: 8 rows per pass, 4 lanes x 4 columns per row
             const long long row_base = (long long)m_tile * GEMM_BM + quarter * 32;
             const int n0 = n_tile * BN + half * COLS_PER_WARP;
             const int sub_row = lane >> 2, sub_col = (lane & 3) * 4;
             const uint32_t stg = smem_u32(sstage + ew * (32 * 16));
-            const uint32_t sb_addr = smem_u32(sb), sg_addr = smem_u32(sg);
             constexpr int NCHUNK = COLS_PER_WARP / 16;
             EpiOperand nxt[4];
             auto fetch_chunk = [&](int c) {
@@ -316,10 +327,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             };
             fetch_chunk(0);  // operands that do not depend on the accumulator: in flight while we wait for the MMAs
+            // bias (and LayerScale gamma) of this lane's 4 columns in each of the NCHUNK chunks: plain read-only loads
+            // issued before the accumulator wait. (A shared-memory staging + block barrier per tile made all eight
+            // epilogue warps rendezvous and cost ~15% on the K=768 forward GEMMs.)
+            float4 bias4[NCHUNK], gam4[(EPI == EPI_RESID_F32) ? NCHUNK : 1];
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int col = n0 + c * 16 + sub_col;
+                bias4[c] = (has_bias && col + 4 <= g.N) ? __ldg(reinterpret_cast<const float4*>(g.bias + col))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                if constexpr (EPI == EPI_RESID_F32)
+                    gam4[c] = (has_gamma && col + 4 <= g.N) ? __ldg(reinterpret_cast<const float4*>(g.gamma + col))
+                                                            : make_float4(1.f, 1.f, 1.f, 1.f);
+            }
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN + half * COLS_PER_WARP;
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < NCHUNK; ++c) {
                 uint32_t r[16];
                 tmem_ld_32x32b_x16(taddr + c * 16, r);
@@ -339,18 +363,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 __syncwarp();
                 // batch every shared-memory read of the chunk before the math / global stores (2 warps per scheduler
                 // cannot hide a load-use chain per element)
-                const int lc = half * COLS_PER_WARP + c * 16 + sub_col;  // column within the N tile
                 float4 v[4];
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
                     const int lr = it * 8 + sub_row;
                     v[it] = lds_f4(stg + (lr * 16 + (((lane & 3) ^ (lr >> 1)) & 3) * 4) * 4);
                 }
-                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (use_vec) {
-                    b4 = lds_f4(sb_addr + lc * 4);
-                    g4 = lds_f4(sg_addr + lc * 4);
-                }
+                const float4 b4 = bias4[c];
+                const float4 g4 = (EPI == EPI_RESID_F32) ? gam4[(EPI == EPI_RESID_F32) ? c : 0]
+                                                         : make_float4(1.f, 1.f, 1.f, 1.f);
                 EpiOperand cur[4];
 #pragma unroll
                 for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
