@@ -27,9 +27,9 @@ extern "C" {
 
 /* GEMM epilogues (vitk_gemm_bf16 `epilogue`) */
 #define VITK_EPI_STORE_BF16 0 /* out_bf16 = acc (+bias)                                              */
-#define VITK_EPI_BIAS_GELU 1  /* pre = acc+bias; out_bf16 = pre; out2_bf16 = gelu(pre)   (Mlp.fc1+act) */
+#define VITK_EPI_BIAS_GELU 1  /* pre = acc+bias; out_bf16 = gelu'(pre) [opt]; out2_bf16 = gelu(pre) (fc1+act) */
 #define VITK_EPI_RESID_F32 2  /* v = acc+bias; [out2_bf16 = v]; out_f32 = resid + gamma*v (proj / fc2)  */
-#define VITK_EPI_DGELU 3      /* out_bf16 = acc * gelu'(aux_bf16)                         (fc2 dgrad)   */
+#define VITK_EPI_DGELU 3      /* out_bf16 = acc * aux_bf16, aux = gelu'(pre) from BIAS_GELU (fc2 dgrad)   */
 #define VITK_EPI_ATOMIC_F32 4 /* out_f32 += acc, split-K                                  (wgrad)       */
 #define VITK_EPI_STORE_F32 5  /* out_f32 = acc (+bias)                                                  */
 #define VITK_EPI_TOKENS_F32 6 /* PatchEmbed token assembly: row (b,p) -> out_f32[b*tok_N+tok_T+p] = acc+bias+pos[tok_T+p] */

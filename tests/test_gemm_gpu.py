@@ -88,8 +88,13 @@ def test_gemm_epilogues():
     pre = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
     act = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
     ops.gemm(a, b, epilogue=ops.EPI_BIAS_GELU, bias=bias, out=pre, out2=act)
-    assert nerr(pre, acc + bias) <= 1e-2
-    assert nerr(act, torch.nn.functional.gelu(acc + bias)) <= 1e-2
+    xp = (acc + bias).clone().requires_grad_(True)           # out = gelu'(pre): what EPI_DGELU multiplies by
+    torch.nn.functional.gelu(xp).sum().backward()
+    assert nerr(pre, xp.grad) <= 4e-3                         # bf16 rounding of values <= 1.13
+    assert nerr(act, torch.nn.functional.gelu(acc + bias)) <= 4e-3
+    # exact-erf GELU in fp32 before the bf16 store: error must be pure bf16 rounding, element by element
+    ref = torch.nn.functional.gelu(acc + bias)
+    assert ((act.float() - ref).abs() <= ref.abs() * 2 ** -8 + 5e-5).all()
 
     o32 = torch.empty((M, N), device="cuda")
     br = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
@@ -100,14 +105,11 @@ def test_gemm_epilogues():
     ops.gemm(a, b, epilogue=ops.EPI_RESID_F32, bias=bias, resid=resid, out=o32b)
     assert nerr(o32b, resid + acc + bias) <= 1e-3
 
-    # dgelu: out = (dY @ W) * gelu'(aux)
+    # dgelu: out = (dY @ W) * aux, aux = gelu'(pre) saved by the forward epilogue
     w = (_mk((K, N), 13) * 0.05).to(torch.bfloat16)   # [K_red, N] -> B mn-major
-    aux = _mk((M, N), 14).to(torch.bfloat16)
     dg = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
-    ops.gemm(a, w, b_mn=True, epilogue=ops.EPI_DGELU, aux=aux, out=dg)
-    xa = aux.float().requires_grad_(True)
-    torch.nn.functional.gelu(xa).sum().backward()
-    assert nerr(dg, (a.float() @ w.float()) * xa.grad) <= 1e-2
+    ops.gemm(a, w, b_mn=True, epilogue=ops.EPI_DGELU, aux=pre, out=dg)
+    assert nerr(dg, (a.float() @ w.float()) * xp.grad) <= 1e-2
 
 
 def test_gemm_strided_views():

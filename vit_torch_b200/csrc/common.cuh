@@ -46,27 +46,88 @@ __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v 
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
 // ----------------------------------------------------------------------------------------------
-// exact-erf GELU (nn.GELU default) and its derivative, fp32.
-// erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7), far below bf16 resolution.
+// packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): one issue slot per two elements
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ float fast_erf(float x) {
-    const float ax = fabsf(x);
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    p *= t;
-    const float r = 1.0f - p * __expf(-ax * ax);
-    return copysignf(r, x);
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_bcast(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_approx_(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ----------------------------------------------------------------------------------------------
+// exact-erf GELU (nn.GELU default) and its derivative, fp32.
+//   gelu(x) = x * Phi(x),  gelu'(x) = Phi(x) + x * phi(x)
+// Phi via Abramowitz-Stegun 26.2.17 (the erf form 7.1.26 rewritten for the normal CDF, |err| <= 7.5e-8, far below
+// bf16 resolution):  Q(|x|) = 1 - Phi(|x|) = phi(|x|) * t * (b1 + b2 t + .. + b5 t^4),  t = 1 / (1 + 0.2316419 |x|)
+//   gelu(x)  = max(x, 0) - |x| * Q
+//   gelu'(x) = step(x) + sign(x) * (|x| phi(|x|) - Q)
+// Both share exp(-x^2/2): 2 MUFU (rcp, ex2) per element; the polynomial runs on packed FFMA2.
+// ----------------------------------------------------------------------------------------------
+template <bool WITH_GRAD>
+__device__ __forceinline__ void gelu_pair(float x0, float x1, float& g0, float& g1, float& d0, float& d1) {
+    constexpr float kInvSqrt2Pi = 0.3989422804014327f;
+    constexpr float B1 = 0.319381530f * kInvSqrt2Pi, B2 = -0.356563782f * kInvSqrt2Pi, B3 = 1.781477937f * kInvSqrt2Pi,
+                    B4 = -1.821255978f * kInvSqrt2Pi, B5 = 1.330274429f * kInvSqrt2Pi;
+    const uint64_t x = f2_pack(x0, x1);
+    const uint64_t nax = f2_pack(-fabsf(x0), -fabsf(x1));
+    float t0, t1;
+    f2_unpack(f2_fma(nax, f2_bcast(-0.2316419f), f2_bcast(1.0f)), t0, t1);
+    const uint64_t t = f2_pack(rcp_approx(t0), rcp_approx(t1));
+    uint64_t p = f2_fma(f2_bcast(B5), t, f2_bcast(B4));
+    p = f2_fma(p, t, f2_bcast(B3));
+    p = f2_fma(p, t, f2_bcast(B2));
+    p = f2_fma(p, t, f2_bcast(B1));
+    p = f2_mul(p, t);
+    float e0, e1;
+    f2_unpack(f2_mul(f2_mul(x, x), f2_bcast(-0.72134752044448170f)), e0, e1);  // -x^2/2 * log2(e)
+    const uint64_t e = f2_pack(ex2_approx_(e0), ex2_approx_(e1));
+    const uint64_t q = f2_mul(e, p);                                            // Q(|x|) = 1 - Phi(|x|)
+    f2_unpack(f2_fma(nax, q, f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), g0, g1);
+    if constexpr (WITH_GRAD) {
+        const uint64_t w = f2_fma(f2_mul(nax, f2_bcast(kInvSqrt2Pi)), e, q);    // Q - |x| phi
+        const uint64_t step = f2_pack(x0 >= 0.f ? 1.f : 0.f, x1 >= 0.f ? 1.f : 0.f);
+        const uint64_t nsgn = f2_fma(step, f2_bcast(-2.0f), f2_bcast(1.0f));    // -sign(x)
+        f2_unpack(f2_fma(w, nsgn, step), d0, d1);
+    }
 }
 __device__ __forceinline__ float gelu_f(float x) {
-    return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f));
+    float g0, g1, d0, d1;
+    gelu_pair<false>(x, x, g0, g1, d0, d1);
+    return g0;
 }
 __device__ __forceinline__ float gelu_grad_f(float x) {
-    const float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f));
-    const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-    return fmaf(x, pdf, cdf);
+    float g0, g1, d0, d1;
+    gelu_pair<true>(x, x, g0, g1, d0, d1);
+    return d0;
 }
 
 // single-instruction exp2 (MUFU.EX2): the softmax loops are issue-bound, exp2f() costs several instructions more

@@ -7,18 +7,19 @@
 // Replaces on the reference path: nn.Linear forward (models/cait.py:99,102,113,126; timm/DINO Attention.qkv/proj,
 // Mlp.fc1/fc2 -- in-repo witness models/swin.py:24-30) and the autograd dgrad / wgrad of the same Linears.
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
-// warps 4..11 = epilogue (two warps per TMEM lane quarter, each taking half of the BN columns).
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 4..11 = epilogue (two warps per TMEM lane quarter = warp % 4, each taking half of the BN columns).
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 namespace vitk {
 
 enum GemmEpilogue : int {
     EPI_STORE_BF16 = 0,  // out_bf16 = acc (+bias)
-    EPI_BIAS_GELU = 1,   // pre = acc + bias ; out_bf16 = pre ; out2_bf16 = gelu(pre)
+    EPI_BIAS_GELU = 1,   // pre = acc + bias ; out_bf16 = gelu'(pre) (saved for backward) ; out2_bf16 = gelu(pre)
     EPI_RESID_F32 = 2,   // v = acc + bias ; [out2_bf16 = v] ; out_f32 = resid + gamma * v   (gamma optional)
-    EPI_DGELU = 3,       // out_bf16 = acc * gelu'(aux_bf16)
+    EPI_DGELU = 3,       // out_bf16 = acc * aux_bf16   (aux = gelu'(pre) saved by EPI_BIAS_GELU)
     EPI_ATOMIC_F32 = 4,  // out_f32 += acc   (red.global.add; split-K wgrad accumulates into the fp32 grad)
     EPI_STORE_F32 = 5,   // out_f32 = acc (+bias)
     EPI_TOKENS_F32 = 6,  // PatchEmbed: row r = (b, p) -> out_f32[b*tok_N + tok_T + p] = acc + bias + pos[tok_T + p]
@@ -62,78 +63,139 @@ template <int BN> struct GemmCfg {
     static constexpr int STAGES = (BN == 256) ? 4 : 6;
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int VEC_BYTES = 2 * 2 * BN * 4;  // double-buffered bias[BN] and gamma[BN] for the epilogue
-    static constexpr int STG_BYTES = GEMM_EPI_WARPS * 32 * 16 * 4;  // per-warp [32 rows x 16 fp32] transpose buffer
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + VEC_BYTES + STG_BYTES + 1024;  // +1 KB: align
+    static constexpr int VEC_BYTES = GEMM_EPI_WARPS * 2 * (BN / 2) * 4;  // per epilogue warp: bias | gamma of its columns
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + VEC_BYTES + 1024;  // +1 KB: align
 };
 
 // ----------------------------------------------------------------------------------------------------------------
-// Epilogue math on 4 consecutive columns of one row, executed in the COALESCED domain: after the accumulator chunk has
-// been transposed through shared memory, the 8 lanes lane/8.. of a warp own 4 columns each of the same row, so that
-// every global load/store instruction touches whole 32-byte sectors of a few rows.
+// Epilogue, executed in the TMEM-native domain: tcgen05.ld 32x32b hands lane l of a warp 16 consecutive accumulator
+// columns of row (quarter * 32 + l). 16 columns are 32 B of bf16 / 64 B of fp32 per lane -- whole 32-byte sectors --
+// and move with the 256-bit global loads / stores of sm_100 (LDG / STG.256): no shared-memory transpose, one row
+// pointer per lane and operand, a single basic block of math per chunk (8 independent fp32x2 pairs of ILP).
+// Chunks that are partial (N tail) or whose pointers are not 32-byte aligned take a 4-column path.
 // ----------------------------------------------------------------------------------------------------------------
-struct EpiOperand {  // operands that do not depend on the accumulator; fetched before the accumulator is waited on
-    float4 r;        // residual (EPI_RESID_F32) / positional embedding (EPI_TOKENS_F32)
-    uint2 aux;       // 4 bf16 pre-activations (EPI_DGELU)
-};
-
-template <int EPI>
-__device__ __forceinline__ void epi_fetch(const GemmArgs& g, EpiOperand& op, long long row, int col) {
-    if constexpr (EPI == EPI_RESID_F32) {
-        if (g.resid != nullptr) op.r = *reinterpret_cast<const float4*>(g.resid + row * g.ldr + col);
-    } else if constexpr (EPI == EPI_DGELU) {
-        op.aux = *reinterpret_cast<const uint2*>(g.aux + row * g.ldaux + col);
-    } else if constexpr (EPI == EPI_TOKENS_F32) {
-        const long long bimg = row / g.tok_n;
-        const int p = static_cast<int>(row - bimg * g.tok_n);
-        op.r = __ldg(reinterpret_cast<const float4*>(g.resid + (long long)(g.tok_T + p) * g.ldr + col));
-    }
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+// L2 prefetch of `bytes` (multiple of 16) at a 16-byte aligned global address
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+template <int EPI> struct EpiTraits {
+    static constexpr bool kBias = (EPI == EPI_STORE_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32 ||
+                                   EPI == EPI_STORE_F32 || EPI == EPI_TOKENS_F32);
+    static constexpr bool kGamma = (EPI == EPI_RESID_F32);
+    static constexpr bool kResid = (EPI == EPI_RESID_F32 || EPI == EPI_TOKENS_F32);  // fp32 operand rows
+    static constexpr bool kAux = (EPI == EPI_DGELU);                                  // bf16 operand rows
+    static constexpr bool kOutF32 = (EPI == EPI_RESID_F32 || EPI == EPI_ATOMIC_F32 || EPI == EPI_STORE_F32 ||
+                                     EPI == EPI_TOKENS_F32);
+    static constexpr bool kColsum = (EPI == EPI_STORE_BF16 || EPI == EPI_DGELU);
+    static constexpr int kOpWords = kResid ? 16 : (kAux ? 8 : 1);  // 32-bit registers of prefetched operand per chunk
+    // operand chunks in flight per warp. DRAM latency is covered by the L2 prefetch of the next tile's operand rows
+    // (issued a whole tile ahead); this ring covers L2 latency.
+    static constexpr int kDepth = (kResid || kAux) ? 4 : 2;
+};
+
+struct EpiRow {  // per-lane row state for one tile; pointers are at (row, first column of this warp)
+    bool ok;                    // row < M
+    float rs;                   // DropPath row scale, 1 when absent
+    void* out;                  // null when the output is skipped
+    __nv_bfloat16* out2;        // null when absent
+    const float* resid;         // null when absent
+    const __nv_bfloat16* aux;
+};
+
+// Epilogue math on 4 consecutive columns of one row. v: accumulators; b / gm: bias / LayerScale gamma (zeros / ones when
+// absent); r: fp32 operand (residual / pos-embed); ax: 4 bf16 operands (GELU'). Outputs: of (fp32 out), oh (bf16 out),
+// oh2 (bf16 out2). Returns the value written to `out` (for the optional column-sum reduction).
 template <int EPI>
-__device__ __forceinline__ float4 epi_apply(const GemmArgs& g, float4 v, long long row, int col, const float4 b,
-                                            const float4 gm, const EpiOperand& op, long long ooff) {
-    // b / gm: bias and LayerScale gamma of these 4 columns (zeros / ones when absent)
-    if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32 ||
-                  EPI == EPI_TOKENS_F32) {
-        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-    }
+__device__ __forceinline__ float4 epi_math4(float4 v, const float4 b, const float4 gm, const float4 r, const uint2 ax,
+                                            const float rs, const bool has_resid, const bool want_dgelu, float4& of,
+                                            uint2& oh, uint2& oh2) {
+    if constexpr (EpiTraits<EPI>::kBias) { v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
     if constexpr (EPI == EPI_STORE_BF16) {
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + ooff + row * g.ldo + col) =
-            make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        oh = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
     } else if constexpr (EPI == EPI_BIAS_GELU) {
-        if (g.out != nullptr)  // pre-activation is only needed for backward
-            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col) =
-                make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out2) + row * g.ldo2 + col) =
-            make_uint2(pack_bf16(gelu_f(v.x), gelu_f(v.y)), pack_bf16(gelu_f(v.z), gelu_f(v.w)));
-    } else if constexpr (EPI == EPI_RESID_F32) {
-        if (g.out2 != nullptr)
-            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out2) + row * g.ldo2 + col) =
-                make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-        v.x *= gm.x; v.y *= gm.y; v.z *= gm.z; v.w *= gm.w;
-        if (g.rowscale != nullptr) {
-            const float rs = __ldg(g.rowscale + row / g.rows_per_sample);
-            v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
+        float g0, g1, g2, g3, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+        if (want_dgelu) {  // gelu'(pre) is only needed for backward
+            gelu_pair<true>(v.x, v.y, g0, g1, d0, d1);
+            gelu_pair<true>(v.z, v.w, g2, g3, d2, d3);
+        } else {
+            gelu_pair<false>(v.x, v.y, g0, g1, d0, d1);
+            gelu_pair<false>(v.z, v.w, g2, g3, d2, d3);
         }
-        if (g.resid != nullptr) { v.x += op.r.x; v.y += op.r.y; v.z += op.r.z; v.w += op.r.w; }
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + row * g.ldo + col) = v;
+        oh = make_uint2(pack_bf16(d0, d1), pack_bf16(d2, d3));
+        oh2 = make_uint2(pack_bf16(g0, g1), pack_bf16(g2, g3));
+    } else if constexpr (EPI == EPI_RESID_F32) {
+        oh2 = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        v.x *= gm.x * rs; v.y *= gm.y * rs; v.z *= gm.z * rs; v.w *= gm.w * rs;
+        if (has_resid) { v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+        of = v;
     } else if constexpr (EPI == EPI_DGELU) {
-        v.x *= gelu_grad_f(bf16_lo(op.aux.x)); v.y *= gelu_grad_f(bf16_hi(op.aux.x));
-        v.z *= gelu_grad_f(bf16_lo(op.aux.y)); v.w *= gelu_grad_f(bf16_hi(op.aux.y));
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col) =
-            make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-    } else if constexpr (EPI == EPI_ATOMIC_F32) {
-        red_add_v4_f32(reinterpret_cast<float*>(g.out) + row * g.ldo + col, v.x, v.y, v.z, v.w);
-    } else if constexpr (EPI == EPI_STORE_F32) {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + ooff + row * g.ldo + col) = v;
+        v.x *= bf16_lo(ax.x); v.y *= bf16_hi(ax.x); v.z *= bf16_lo(ax.y); v.w *= bf16_hi(ax.y);
+        oh = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
     } else if constexpr (EPI == EPI_TOKENS_F32) {
-        const long long bimg = row / g.tok_n;
-        const int p = static_cast<int>(row - bimg * g.tok_n);
-        v.x += op.r.x; v.y += op.r.y; v.z += op.r.z; v.w += op.r.w;
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + (bimg * g.tok_N + g.tok_T + p) * g.ldo + col) = v;
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        of = v;
+    } else {  // EPI_ATOMIC_F32 / EPI_STORE_F32
+        of = v;
     }
-    return v;  // the value written to `out` (for STORE_* / DGELU / ATOMIC; used by the optional column-sum reduction)
+    return v;
+}
+
+// Column sums over the 32 rows of a warp for the 16 columns of a chunk (lane = row): recursive halving, 16 shuffles.
+// On return lane l (l even) holds the total of column ((l >> 1) & 15) ... see `col_of_lane`.
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+    float a[8];
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float send = up ? v[i] : v[i + 8];
+            const float keep = up ? v[i + 8] : v[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    float b4[4];
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = up ? a[i] : a[i + 4];
+            const float keep = up ? a[i + 4] : a[i];
+            b4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    float c2[2];
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = up ? b4[i] : b4[i + 2];
+            const float keep = up ? b4[i + 2] : b4[i];
+            c2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    float d;
+    {
+        const bool up = lane & 2;
+        const float send = up ? c2[0] : c2[1];
+        const float keep = up ? c2[1] : c2[0];
+        d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;  // column index held by this lane: 8*bit4 + 4*bit3 + 2*bit2 + bit1 of `lane`
+}
+__device__ __forceinline__ int warp_colsum16_col(int lane) {
+    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
@@ -153,8 +215,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
     uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]   epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-    float* svec = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);  // [2][bias BN | gamma BN]
-    float* sstage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + Cfg::VEC_BYTES);
+    float* svec = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);  // per-warp bias | gamma
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -174,7 +235,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    __syncwarp();
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -293,114 +355,244 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp >= GEMM_EPI_WARP0) {
         // ===================== epilogue =====================
+        using T = EpiTraits<EPI>;
         const int ew = warp - GEMM_EPI_WARP0;
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
         const int half = ew >> 2;      // which half of the BN columns
         constexpr int COLS_PER_WARP = BN / 2;
+        constexpr int NCHUNK = COLS_PER_WARP / 16;
+        constexpr int PF = T::kDepth < NCHUNK ? T::kDepth : NCHUNK;
+        static_assert(NCHUNK % PF == 0 && PF % 2 == 0, "prefetch ring must tile the chunk loop");
+        constexpr int OUT_ESZ = T::kOutF32 ? 4 : 2;
         int as = 0;
         uint32_t aphase = 0;
-        const int et = threadIdx.x - GEMM_EPI_WARP0 * 32;  // 0..255 within the epilogue warps
-        constexpr bool kUsesVec = (EPI == EPI_STORE_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32 ||
-                                   EPI == EPI_STORE_F32 || EPI == EPI_TOKENS_F32);
-        for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-            const int n_tile = u % g.num_n_tiles;
-            const int rest = u / g.num_n_tiles;
-            const int mb = rest / g.splits;
+        // per-warp staging of this tile's bias / gamma columns: [bias COLS_PER_WARP | gamma COLS_PER_WARP]
+        float* wvec = svec + ew * (2 * COLS_PER_WARP);
+        const uint32_t wvec_s = smem_u32(wvec);
+        const bool has_bias = T::kBias && g.bias != nullptr;
+        const bool has_gamma = T::kGamma && g.gamma != nullptr;
+        const bool has_resid = T::kResid && g.resid != nullptr;
+        const bool want_out = g.out != nullptr;
+        // 256-bit accesses need 32-byte aligned row segments (chunk starts are multiples of 16 columns)
+        auto aligned32 = [](const void* ptr, long long ld, int esz) {
+            return ptr == nullptr || (((reinterpret_cast<uintptr_t>(ptr) | (uintptr_t)(ld * esz)) & 31) == 0);
+        };
+        const bool vec_ok_static = aligned32(g.out, g.ldo, OUT_ESZ) && aligned32(g.out2, g.ldo2, 2) &&
+                                   (!T::kResid || aligned32(g.resid, g.ldr, 4)) &&
+                                   (!T::kAux || aligned32(g.aux, g.ldaux, 2)) &&
+                                   ((g.so_h * OUT_ESZ) & 31) == 0 && ((g.so_b * OUT_ESZ) & 31) == 0;
+
+        // row state of tile unit `un` for this lane
+        auto make_row = [&](int un, EpiRow& R, int& n0) {
+            const int n_tile = un % g.num_n_tiles;
+            const int mb = (un / g.num_n_tiles) / g.splits;
             const int m_tile = mb % g.num_m_tiles;
             const int batch = mb / g.num_m_tiles;
             const long long ooff = (long long)(batch % g.nbatch_h) * g.so_h + (long long)(batch / g.nbatch_h) * g.so_b;
-            const bool has_bias = kUsesVec && g.bias != nullptr;
-            const bool has_gamma = (EPI == EPI_RESID_F32) && g.gamma != nullptr;
-            // coalesced-domain coordinates of this lane: 8 rows per pass, 4 lanes x 4 columns per row
-            const long long row_base = (long long)m_tile * GEMM_BM + quarter * 32;
-            const int n0 = n_tile * BN + half * COLS_PER_WARP;
-            const int sub_row = lane >> 2, sub_col = (lane & 3) * 4;
-            const uint32_t stg = smem_u32(sstage + ew * (32 * 16));
-            constexpr int NCHUNK = COLS_PER_WARP / 16;
-            EpiOperand nxt[4];
-            auto fetch_chunk = [&](int c) {
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const long long rr = row_base + it * 8 + sub_row;
-                    const int col = n0 + c * 16 + sub_col;
-                    if (rr < g.M && col + 4 <= g.N) epi_fetch<EPI>(g, nxt[it], rr, col);
+            const long long row = (long long)m_tile * GEMM_BM + quarter * 32 + lane;
+            n0 = n_tile * BN + half * COLS_PER_WARP;
+            R.ok = row < g.M;
+            R.rs = 1.0f;
+            R.out2 = nullptr; R.resid = nullptr; R.aux = nullptr;
+            long long orow = row;  // output row
+            if constexpr (EPI == EPI_TOKENS_F32) {
+                const long long bimg = row / g.tok_n;
+                const int pp = static_cast<int>(row - bimg * g.tok_n);
+                orow = bimg * g.tok_N + g.tok_T + pp;
+                R.resid = g.resid + (long long)(g.tok_T + pp) * g.ldr + n0;  // pos_embed row
+            } else if constexpr (EPI == EPI_RESID_F32) {
+                if (has_resid) R.resid = g.resid + row * g.ldr + n0;
+                if (g.out2 != nullptr) R.out2 = reinterpret_cast<__nv_bfloat16*>(g.out2) + row * g.ldo2 + n0;
+                if (g.rowscale != nullptr && R.ok) R.rs = __ldg(g.rowscale + row / g.rows_per_sample);
+            } else if constexpr (EPI == EPI_BIAS_GELU) {
+                R.out2 = reinterpret_cast<__nv_bfloat16*>(g.out2) + row * g.ldo2 + n0;
+            } else if constexpr (EPI == EPI_DGELU) {
+                R.aux = g.aux + row * g.ldaux + n0;
+            }
+            R.out = want_out ? static_cast<void*>(reinterpret_cast<char*>(g.out) + (ooff + orow * g.ldo + n0) * OUT_ESZ)
+                             : nullptr;
+        };
+        // L2 prefetch of the accumulator-independent operand rows (residual / GELU') of a future tile
+        auto l2_prefetch_unit = [&](int un) {
+            if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_DGELU) {
+                if (un >= num_units) return;
+                EpiRow R;
+                int n0;
+                make_row(un, R, n0);
+                const int nc = min(COLS_PER_WARP, g.N - n0) & ~7;  // 16-byte multiples for both element sizes
+                if (!R.ok || nc <= 0) return;
+                if constexpr (EPI == EPI_RESID_F32) {
+                    if (R.resid != nullptr) prefetch_l2_bulk(R.resid, nc * 4);
+                } else {
+                    prefetch_l2_bulk(R.aux, nc * 2);
+                }
+            }
+        };
+        l2_prefetch_unit(blockIdx.x);
+
+        for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+            l2_prefetch_unit(u + gridDim.x);  // a whole tile of lead time
+            EpiRow R;
+            int n0;
+            make_row(u, R, n0);
+            const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN + half * COLS_PER_WARP;
+
+            // stage bias / gamma of this warp's columns (zero / one padded beyond N)
+            if constexpr (T::kBias) {
+                if (lane * 4 < COLS_PER_WARP) {
+                    const int col = n0 + lane * 4;
+                    const float4 bv = (has_bias && col + 4 <= g.N) ? __ldg(reinterpret_cast<const float4*>(g.bias + col))
+                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(wvec + lane * 4) = bv;
+                    if constexpr (T::kGamma) {
+                        const float4 gv = (has_gamma && col + 4 <= g.N)
+                                              ? __ldg(reinterpret_cast<const float4*>(g.gamma + col))
+                                              : make_float4(1.f, 1.f, 1.f, 1.f);
+                        *reinterpret_cast<float4*>(wvec + COLS_PER_WARP + lane * 4) = gv;
+                    }
+                }
+                __syncwarp();
+            }
+
+            // operand ring: chunk c's residual / GELU' segment of this lane's row (vector path only)
+            uint32_t opq[PF][T::kOpWords];
+            auto chunk_is_vec = [&](int c) { return vec_ok_static && n0 + c * 16 + 16 <= g.N; };
+            auto fetch_chunk = [&](int c, uint32_t* dst) {
+                if (!R.ok || !chunk_is_vec(c)) return;
+                if constexpr (T::kResid) {
+                    if (R.resid != nullptr) {
+                        ldg256(R.resid + c * 16, dst);
+                        ldg256(R.resid + c * 16 + 8, dst + 8);
+                    }
+                } else if constexpr (T::kAux) {
+                    ldg256(R.aux + c * 16, dst);
                 }
             };
-            fetch_chunk(0);  // operands that do not depend on the accumulator: in flight while we wait for the MMAs
-            // bias (and LayerScale gamma) of this lane's 4 columns in each of the NCHUNK chunks: plain read-only loads
-            // issued before the accumulator wait. (A shared-memory staging + block barrier per tile made all eight
-            // epilogue warps rendezvous and cost ~15% on the K=768 forward GEMMs.)
-            float4 bias4[NCHUNK], gam4[(EPI == EPI_RESID_F32) ? NCHUNK : 1];
 #pragma unroll
-            for (int c = 0; c < NCHUNK; ++c) {
-                const int col = n0 + c * 16 + sub_col;
-                bias4[c] = (has_bias && col + 4 <= g.N) ? __ldg(reinterpret_cast<const float4*>(g.bias + col))
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-                if constexpr (EPI == EPI_RESID_F32)
-                    gam4[c] = (has_gamma && col + 4 <= g.N) ? __ldg(reinterpret_cast<const float4*>(g.gamma + col))
-                                                            : make_float4(1.f, 1.f, 1.f, 1.f);
-            }
+            for (int j = 0; j < PF; ++j) fetch_chunk(j, opq[j]);  // in flight while we wait for the MMAs
+
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN + half * COLS_PER_WARP;
+            uint32_t racc[2][16];
+            tmem_ld_32x32b_x16(taddr, racc[0]);
+#pragma unroll 1
+            for (int c0 = 0; c0 < NCHUNK; c0 += PF) {
 #pragma unroll
-            for (int c = 0; c < NCHUNK; ++c) {
-                uint32_t r[16];
-                tmem_ld_32x32b_x16(taddr + c * 16, r);
-                tmem_ld_wait();
-                if (c == NCHUNK - 1) {
-                    // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[as]);
-                }
-                // transpose through shared memory: TMEM domain (lane == row) -> coalesced domain. 16-byte units are
-                // XOR-swizzled with (row >> 1) so that both the row-wise writes and the 8-row reads are conflict free.
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    sts_u4(stg + (lane * 16 + ((u ^ (lane >> 1)) & 3) * 4) * 4, r[u * 4 + 0], r[u * 4 + 1], r[u * 4 + 2],
-                           r[u * 4 + 3]);
-                __syncwarp();
-                // batch every shared-memory read of the chunk before the math / global stores (2 warps per scheduler
-                // cannot hide a load-use chain per element)
-                float4 v[4];
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int lr = it * 8 + sub_row;
-                    v[it] = lds_f4(stg + (lr * 16 + (((lane & 3) ^ (lr >> 1)) & 3) * 4) * 4);
-                }
-                const float4 b4 = bias4[c];
-                const float4 g4 = (EPI == EPI_RESID_F32) ? gam4[(EPI == EPI_RESID_F32) ? c : 0]
-                                                         : make_float4(1.f, 1.f, 1.f, 1.f);
-                EpiOperand cur[4];
-#pragma unroll
-                for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
-                if (c + 1 < NCHUNK) fetch_chunk(c + 1);
-                float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const long long rr = row_base + it * 8 + sub_row;
-                    const int col = n0 + c * 16 + sub_col;
-                    if (rr < g.M && col + 4 <= g.N) {
-                        const float4 w = epi_apply<EPI>(g, v[it], rr, col, b4, g4, cur[it], ooff);
-                        cs.x += w.x; cs.y += w.y; cs.z += w.z; cs.w += w.w;
+                for (int j = 0; j < PF; ++j) {
+                    const int c = c0 + j;
+                    const uint32_t* r = racc[j & 1];
+                    tmem_ld_wait();
+                    if (c + 1 < NCHUNK) {
+                        // the accumulator chunk is fetched one chunk ahead of its use
+                        tmem_ld_32x32b_x16(taddr + (c + 1) * 16, racc[(j + 1) & 1]);
+                    } else {
+                        // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[as]);
                     }
-                }
-                if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_DGELU) {
-                    if (g.colsum != nullptr) {
-                        // reduce over the warp's 32 rows: lanes with equal (lane & 3) own the same 4 columns
+                    const int col0 = n0 + c * 16;
+                    if (col0 >= g.N) continue;  // (warp-uniform)
+                    float cs[16];
+                    if (chunk_is_vec(c)) {
+                        // ---- vector path: 16 columns, 256-bit global accesses
+                        uint32_t ho[8], ho2[8], fo[16];
 #pragma unroll
-                        for (int o = 4; o < 32; o <<= 1) {
-                            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o);
-                            cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
-                            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o);
-                            cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                         __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), r4 = b4;
+                            uint2 ax = make_uint2(0u, 0u);
+                            if constexpr (T::kBias) b4 = lds_f4(wvec_s + (c * 16 + 4 * q) * 4);
+                            if constexpr (T::kGamma) g4 = lds_f4(wvec_s + (COLS_PER_WARP + c * 16 + 4 * q) * 4);
+                            if constexpr (T::kResid)
+                                r4 = make_float4(__uint_as_float(opq[j][4 * q]), __uint_as_float(opq[j][4 * q + 1]),
+                                                 __uint_as_float(opq[j][4 * q + 2]), __uint_as_float(opq[j][4 * q + 3]));
+                            if constexpr (T::kAux) ax = make_uint2(opq[j][2 * q], opq[j][2 * q + 1]);
+                            float4 of;
+                            uint2 oh, oh2;
+                            const float4 w = epi_math4<EPI>(v, b4, g4, r4, ax, R.rs, R.resid != nullptr, want_out, of, oh, oh2);
+                            cs[4 * q] = w.x; cs[4 * q + 1] = w.y; cs[4 * q + 2] = w.z; cs[4 * q + 3] = w.w;
+                            if constexpr (T::kOutF32) {
+                                fo[4 * q] = __float_as_uint(of.x); fo[4 * q + 1] = __float_as_uint(of.y);
+                                fo[4 * q + 2] = __float_as_uint(of.z); fo[4 * q + 3] = __float_as_uint(of.w);
+                            } else {
+                                ho[2 * q] = oh.x; ho[2 * q + 1] = oh.y;
+                            }
+                            if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32) {
+                                ho2[2 * q] = oh2.x; ho2[2 * q + 1] = oh2.y;
+                            }
                         }
-                        const int col = n0 + c * 16 + sub_col;
-                        if (lane < 4 && col + 4 <= g.N) red_add_v4_f32(g.colsum + col, cs.x, cs.y, cs.z, cs.w);
+                        if (R.ok) {
+                            if constexpr (EPI == EPI_ATOMIC_F32) {
+                                float* o = reinterpret_cast<float*>(R.out) + c * 16;
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    red_add_v4_f32(o + 4 * q, __uint_as_float(fo[4 * q]), __uint_as_float(fo[4 * q + 1]),
+                                                   __uint_as_float(fo[4 * q + 2]), __uint_as_float(fo[4 * q + 3]));
+                            } else if constexpr (T::kOutF32) {
+                                float* o = reinterpret_cast<float*>(R.out) + c * 16;
+                                stg256(o, fo);
+                                stg256(o + 8, fo + 8);
+                            } else {
+                                if (R.out != nullptr) stg256(reinterpret_cast<__nv_bfloat16*>(R.out) + c * 16, ho);
+                            }
+                            if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32) {
+                                if (R.out2 != nullptr) stg256(R.out2 + c * 16, ho2);
+                            }
+                        }
+                        if (c + PF < NCHUNK) fetch_chunk(c + PF, opq[j]);  // refill the ring slot just consumed
+                    } else {
+                        // ---- 4-column path: N tail or unaligned pointers
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int cw = c * 16 + 4 * q;  // column within this warp's range
+                            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (n0 + cw + 4 <= g.N) {
+                                const float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                             __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), r4 = b4;
+                                uint2 ax = make_uint2(0u, 0u);
+                                if constexpr (T::kBias) b4 = lds_f4(wvec_s + cw * 4);
+                                if constexpr (T::kGamma) g4 = lds_f4(wvec_s + (COLS_PER_WARP + cw) * 4);
+                                if (R.ok) {
+                                    if constexpr (T::kResid) {
+                                        if (R.resid != nullptr) r4 = *reinterpret_cast<const float4*>(R.resid + cw);
+                                    }
+                                    if constexpr (T::kAux) ax = *reinterpret_cast<const uint2*>(R.aux + cw);
+                                }
+                                float4 of;
+                                uint2 oh, oh2;
+                                w = epi_math4<EPI>(v, b4, g4, r4, ax, R.rs, R.resid != nullptr, want_out, of, oh, oh2);
+                                if (R.ok) {
+                                    if constexpr (EPI == EPI_ATOMIC_F32) {
+                                        red_add_v4_f32(reinterpret_cast<float*>(R.out) + cw, of.x, of.y, of.z, of.w);
+                                    } else if constexpr (T::kOutF32) {
+                                        *reinterpret_cast<float4*>(reinterpret_cast<float*>(R.out) + cw) = of;
+                                    } else {
+                                        if (R.out != nullptr)
+                                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(R.out) + cw) = oh;
+                                    }
+                                    if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32) {
+                                        if (R.out2 != nullptr) *reinterpret_cast<uint2*>(R.out2 + cw) = oh2;
+                                    }
+                                }
+                            }
+                            cs[4 * q] = w.x; cs[4 * q + 1] = w.y; cs[4 * q + 2] = w.z; cs[4 * q + 3] = w.w;
+                        }
+                    }
+                    if constexpr (T::kColsum) {
+                        if (g.colsum != nullptr) {
+                            if (!R.ok) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) cs[i] = 0.f;
+                            }
+                            const float tot = warp_colsum16(cs, lane);
+                            const int col = col0 + warp_colsum16_col(lane);
+                            if ((lane & 1) == 0 && col < g.N) atomicAdd(g.colsum + col, tot);
+                        }
                     }
                 }
-                __syncwarp();
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
@@ -408,7 +600,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == 1) {
         tc_fence_after_sync();
         tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
