@@ -86,38 +86,74 @@ __device__ __forceinline__ float ex2_approx_(float x) {
 // ----------------------------------------------------------------------------------------------
 // exact-erf GELU (nn.GELU default) and its derivative, fp32.
 //   gelu(x) = x * Phi(x),  gelu'(x) = Phi(x) + x * phi(x)
-// Phi via Abramowitz-Stegun 26.2.17 (the erf form 7.1.26 rewritten for the normal CDF, |err| <= 7.5e-8, far below
-// bf16 resolution):  Q(|x|) = 1 - Phi(|x|) = phi(|x|) * t * (b1 + b2 t + .. + b5 t^4),  t = 1 / (1 + 0.2316419 |x|)
+// With Q(|x|) = 1 - Phi(|x|) = exp(-x^2/2) * P(|x|), P = Mills ratio / sqrt(2 pi):
 //   gelu(x)  = max(x, 0) - |x| * Q
-//   gelu'(x) = step(x) + sign(x) * (|x| phi(|x|) - Q)
-// Both share exp(-x^2/2): 2 MUFU (rcp, ex2) per element; the polynomial runs on packed FFMA2.
+//   gelu'(x) = step(x) - sign(x) * exp(-x^2/2) * (P(|x|) - |x| / sqrt(2 pi))
+// P is a degree-8 polynomial on [0, 6] (weighted minimax fit, |error in Q| and |x| * |error in Q| <= 1.8e-6 -- three
+// orders below bf16 resolution of the outputs; beyond 6 the argument is clamped, exp(-18) = 1.5e-8 makes Q vanish).
+// One MUFU (ex2) per element; the polynomial runs on packed FFMA2. `gelu_pairs<NP>` evaluates NP pairs in lock step
+// (step-major order) so that the dependent Horner chains of different pairs interleave in the instruction stream.
 // ----------------------------------------------------------------------------------------------
+template <int NP, bool WITH_GRAD>
+__device__ __forceinline__ void gelu_pairs(const float* x, float* g, float* d) {
+    constexpr float C0 = 4.999982417e-01f, C1 = -3.988357782e-01f, C2 = 2.489434332e-01f, C3 = -1.289402843e-01f,
+                    C4 = 5.464975536e-02f, C5 = -1.768272184e-02f, C6 = 3.933028784e-03f, C7 = -5.189787480e-04f,
+                    C8 = 3.003616439e-05f;
+    constexpr float kInvSqrt2Pi = 0.3989422804014327f;
+    uint64_t xx[NP], ax[NP], axc[NP], e[NP], p[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const float a0 = fabsf(x[2 * i]), a1 = fabsf(x[2 * i + 1]);
+        xx[i] = f2_pack(x[2 * i], x[2 * i + 1]);
+        ax[i] = f2_pack(a0, a1);
+        axc[i] = f2_pack(fminf(a0, 6.0f), fminf(a1, 6.0f));
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) e[i] = f2_mul(f2_mul(xx[i], xx[i]), f2_bcast(-0.72134752044448170f));  // -x^2/2 log2 e
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        float e0, e1;
+        f2_unpack(e[i], e0, e1);
+        e[i] = f2_pack(ex2_approx_(e0), ex2_approx_(e1));
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) p[i] = f2_fma(f2_bcast(C8), axc[i], f2_bcast(C7));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) p[i] = f2_fma(p[i], axc[i], f2_bcast(C6));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) p[i] = f2_fma(p[i], axc[i], f2_bcast(C5));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) p[i] = f2_fma(p[i], axc[i], f2_bcast(C4));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) p[i] = f2_fma(p[i], axc[i], f2_bcast(C3));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) p[i] = f2_fma(p[i], axc[i], f2_bcast(C2));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) p[i] = f2_fma(p[i], axc[i], f2_bcast(C1));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) p[i] = f2_fma(p[i], axc[i], f2_bcast(C0));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const uint64_t q = f2_mul(e[i], p[i]);  // Q(|x|)
+        const uint64_t nq = f2_mul(q, f2_bcast(-1.0f));
+        f2_unpack(f2_fma(ax[i], nq, f2_pack(fmaxf(x[2 * i], 0.f), fmaxf(x[2 * i + 1], 0.f))), g[2 * i], g[2 * i + 1]);
+    }
+    if constexpr (WITH_GRAD) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            const uint64_t w = f2_mul(e[i], f2_fma(ax[i], f2_bcast(-kInvSqrt2Pi), p[i]));  // Q - |x| phi
+            const uint64_t step = f2_pack(x[2 * i] >= 0.f ? 1.f : 0.f, x[2 * i + 1] >= 0.f ? 1.f : 0.f);
+            const uint64_t nsgn = f2_fma(step, f2_bcast(-2.0f), f2_bcast(1.0f));  // -sign(x)
+            f2_unpack(f2_fma(w, nsgn, step), d[2 * i], d[2 * i + 1]);
+        }
+    }
+}
 template <bool WITH_GRAD>
 __device__ __forceinline__ void gelu_pair(float x0, float x1, float& g0, float& g1, float& d0, float& d1) {
-    constexpr float kInvSqrt2Pi = 0.3989422804014327f;
-    constexpr float B1 = 0.319381530f * kInvSqrt2Pi, B2 = -0.356563782f * kInvSqrt2Pi, B3 = 1.781477937f * kInvSqrt2Pi,
-                    B4 = -1.821255978f * kInvSqrt2Pi, B5 = 1.330274429f * kInvSqrt2Pi;
-    const uint64_t x = f2_pack(x0, x1);
-    const uint64_t nax = f2_pack(-fabsf(x0), -fabsf(x1));
-    float t0, t1;
-    f2_unpack(f2_fma(nax, f2_bcast(-0.2316419f), f2_bcast(1.0f)), t0, t1);
-    const uint64_t t = f2_pack(rcp_approx(t0), rcp_approx(t1));
-    uint64_t p = f2_fma(f2_bcast(B5), t, f2_bcast(B4));
-    p = f2_fma(p, t, f2_bcast(B3));
-    p = f2_fma(p, t, f2_bcast(B2));
-    p = f2_fma(p, t, f2_bcast(B1));
-    p = f2_mul(p, t);
-    float e0, e1;
-    f2_unpack(f2_mul(f2_mul(x, x), f2_bcast(-0.72134752044448170f)), e0, e1);  // -x^2/2 * log2(e)
-    const uint64_t e = f2_pack(ex2_approx_(e0), ex2_approx_(e1));
-    const uint64_t q = f2_mul(e, p);                                            // Q(|x|) = 1 - Phi(|x|)
-    f2_unpack(f2_fma(nax, q, f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), g0, g1);
-    if constexpr (WITH_GRAD) {
-        const uint64_t w = f2_fma(f2_mul(nax, f2_bcast(kInvSqrt2Pi)), e, q);    // Q - |x| phi
-        const uint64_t step = f2_pack(x0 >= 0.f ? 1.f : 0.f, x1 >= 0.f ? 1.f : 0.f);
-        const uint64_t nsgn = f2_fma(step, f2_bcast(-2.0f), f2_bcast(1.0f));    // -sign(x)
-        f2_unpack(f2_fma(w, nsgn, step), d0, d1);
-    }
+    const float x[2] = {x0, x1};
+    float g[2], d[2] = {0.f, 0.f};
+    gelu_pairs<1, WITH_GRAD>(x, g, d);
+    g0 = g[0]; g1 = g[1]; d0 = d[0]; d1 = d[1];
 }
 __device__ __forceinline__ float gelu_f(float x) {
     float g0, g1, d0, d1;
@@ -263,6 +299,61 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// CTA-pair (cta_group::2) variants: the two CTAs of a 2-CTA cluster execute one UMMA of M = 256 (each CTA owns 128
+// rows of A and D and half of the B tile). Shared-memory addresses with bit 24 cleared name the same offset in the
+// leader (even-ranked) CTA of the pair.
+// ----------------------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <uint32_t kCols> __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst) {
+    static_assert(kCols >= 32 && kCols <= 512 && (kCols & (kCols - 1)) == 0, "TMEM cols: pow2 in [32,512]");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols> __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// TMA load into this CTA's shared memory whose completion bytes are counted on the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_2cta(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+// arrive on the leader CTA's copy of `bar` (works from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+// arrives on `bar` in BOTH CTAs of the pair once all previously issued cta_group::2 MMAs have completed
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(static_cast<uint16_t>(3))
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }

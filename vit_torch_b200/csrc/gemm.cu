@@ -1,5 +1,6 @@
 // Host launcher + C-ABI entry for the tcgen05 GEMM (see gemm.cuh for the kernel).
 #include "gemm.cuh"
+#include "gemm2.cuh"
 #include "tmap.cuh"
 #include "../../include/vitk.h"
 #include <stdlib.h>
@@ -40,6 +41,58 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     const int grid = units < sm_count() ? units : sm_count();
     kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
+// ---- CTA-pair kernel (gemm2.cuh) ----
+static int max_clusters() {
+    static int cached = 0;
+    if (cached == 0) cached = sm_count() / 2 > 0 ? sm_count() / 2 : 1;
+    return cached;
+}
+
+// VITK_GEMM_2CTA=0 keeps every GEMM on the 1-CTA kernel (A/B measurements)
+static bool use_2cta() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VITK_GEMM_2CTA");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
+    using Cfg = Gemm2Cfg;
+    auto kern = gemm2_bf16_kernel<A_MN, B_MN, EPI>;
+    static bool attr_set = false;  // benign race: idempotent
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+            return VITK_ERR_CUDA;
+        attr_set = true;
+    }
+    const int units = ((g.num_m_tiles + 1) / 2) * g.num_n_tiles * g.splits;
+    const int clusters = units < max_clusters() ? units : max_clusters();
+    kern<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);  // static __cluster_dims__(2,1,1)
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
+static int dispatch_gemm2(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g,
+                          cudaStream_t s) {
+#define VITK_CASE2(AM, BM_, E)                                 \
+    if (a_mn == (AM) && b_mn == (BM_) && epi == (E)) return launch_gemm2<(AM) != 0, (BM_) != 0, (E)>(tmA, tmB, g, s);
+    VITK_CASE2(0, 0, EPI_STORE_BF16)
+    VITK_CASE2(0, 0, EPI_BIAS_GELU)
+    VITK_CASE2(0, 0, EPI_RESID_F32)
+    VITK_CASE2(0, 1, EPI_STORE_BF16)
+    VITK_CASE2(0, 1, EPI_DGELU)
+    VITK_CASE2(1, 1, EPI_ATOMIC_F32)
+#undef VITK_CASE2
+    return VITK_ERR_UNSUPPORTED;
+}
+static bool gemm2_supported(int a_mn, int b_mn, int epi) {
+    return (a_mn == 0 && b_mn == 0 && (epi == EPI_STORE_BF16 || epi == EPI_BIAS_GELU || epi == EPI_RESID_F32)) ||
+           (a_mn == 0 && b_mn == 1 && (epi == EPI_STORE_BF16 || epi == EPI_DGELU)) ||
+           (a_mn == 1 && b_mn == 1 && epi == EPI_ATOMIC_F32);
 }
 
 template <int BN>
@@ -98,6 +151,19 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
     if (rowscale != nullptr && rows_per_sample <= 0) return VITK_ERR_ARG;
     if (epilogue == EPI_TOKENS_F32 && (tok_n <= 0 || tok_N < tok_n + tok_T || resid == nullptr)) return VITK_ERR_ARG;
     const int BN = (Nepi % 256 == 0 || Nepi >= 1024) ? 256 : 128;
+    // large plain GEMMs run on the CTA-pair kernel (256 x 256 tiles per 2-CTA cluster)
+    // ... when wave quantisation does not eat the gain: a pair unit is 256 rows, so e.g. 197 row tiles x 3 column tiles
+    // are 297 units on 74 clusters (4.01 waves) against 591 tiles on 148 SMs (3.99 waves). Measured (sustained clocks):
+    // +7 % on N = 2304 / 3072 forward GEMMs, -6 % on N = 768, wgrad (MN-major A, split-K) even.
+    bool pair = use_2cta() && BN == 256 && bt.nh * bt.nb == 1 && M >= 1024 && a_mn_major == 0 &&
+                gemm2_supported(a_mn_major != 0, b_mn_major != 0, epilogue);
+    if (pair) {
+        const long long mt = (M + GEMM_BM - 1) / GEMM_BM, nt = (Nepi + BN - 1) / BN;
+        const long long u1 = mt * nt, u2 = ((mt + 1) / 2) * nt;
+        const long long w1 = (u1 + sm_count() - 1) / sm_count(), w2 = (u2 + max_clusters() - 1) / max_clusters();
+        const double eff1 = (double)u1 / (double)(w1 * sm_count()), eff2 = (double)(mt * nt) / (double)(w2 * 2 * max_clusters());
+        pair = eff2 >= 0.9 * eff1;
+    }
 
     GemmArgs g;
     g.M = M; g.N = Nepi; g.K = K;
@@ -106,7 +172,10 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
     g.num_kblocks = (K + GEMM_BK - 1) / GEMM_BK;
     const bool accumulate = (epilogue == EPI_ATOMIC_F32);
     int s = 1;
-    if (accumulate) s = splits > 0 ? splits : choose_splits(g.num_m_tiles * g.num_n_tiles, g.num_kblocks, sm_count());
+    if (accumulate)
+        s = splits > 0 ? splits
+                       : (pair ? choose_splits(((g.num_m_tiles + 1) / 2) * g.num_n_tiles, g.num_kblocks, max_clusters())
+                               : choose_splits(g.num_m_tiles * g.num_n_tiles, g.num_kblocks, sm_count()));
     if (s > g.num_kblocks) s = g.num_kblocks;
     g.kblocks_per_split = (g.num_kblocks + s - 1) / s;
     g.splits = (g.num_kblocks + g.kblocks_per_split - 1) / g.kblocks_per_split;
@@ -117,6 +186,11 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
     g.tok_n = tok_n; g.tok_N = tok_N; g.tok_T = tok_T;
     g.nbatch_h = bt.nh; g.nbatch_b = bt.nb; g.so_h = bt.so_h; g.so_b = bt.so_b;
     g.colsum = colsum;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("VITK_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+        g.dbg = dbg;
+    }
     if (colsum != nullptr && !(epilogue == EPI_STORE_BF16 || epilogue == EPI_DGELU)) return VITK_ERR_UNSUPPORTED;
     if (bt.nh < 1 || bt.nb < 1) return VITK_ERR_ARG;
     if ((bt.sa_h | bt.sa_b | bt.sb_h | bt.sb_b) % 8 != 0) return VITK_ERR_ARG;
@@ -134,7 +208,8 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
         if (!a_mn_major) rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM);
         else             rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, GEMM_BK);
         if (rc) return VITK_ERR_TMAP;
-        if (!b_mn_major) rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GEMM_BK, (uint32_t)BN);
+        if (!b_mn_major) rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GEMM_BK,
+                                                (uint32_t)(pair ? BN / 2 : BN));  // pair: each CTA loads half of the B tile
         else             rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BK);
         if (rc) return VITK_ERR_TMAP;
     } else {
@@ -147,6 +222,7 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
     }
 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (pair) return dispatch_gemm2(a_mn_major != 0, b_mn_major != 0, epilogue, tmA, tmB, g, st);
     if (BN == 256) return dispatch_gemm<256>(a_mn_major != 0, b_mn_major != 0, epilogue, tmA, tmB, g, st);
     return dispatch_gemm<128>(a_mn_major != 0, b_mn_major != 0, epilogue, tmA, tmB, g, st);
 }

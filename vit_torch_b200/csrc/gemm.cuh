@@ -47,6 +47,7 @@ struct GemmArgs {
     int nbatch_h, nbatch_b;
     long long so_h, so_b;    // out strides (elements) per inner / outer batch index
     int a_perm[3], b_perm[3];  // tensor-map dim 1+i takes logical coordinate perm[i] (0 = row, 1 = batch_h, 2 = batch_b)
+    int dbg;        // VITK_GEMM_DBG experiment switches (0 in production): 1 no L2 prefetch, 2 plain loads, 4 no loads, 8 no stores
     float* colsum;  // optional fp32 [N]: += column sums of the values stored to `out` (bias gradient of the next Linear)
 };
 
@@ -76,6 +77,11 @@ template <int BN> struct GemmCfg {
 // ----------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
     asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void ldg256_plain(const void* p, uint32_t* r) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "l"(p));
 }
@@ -116,16 +122,15 @@ struct EpiRow {  // per-lane row state for one tile; pointers are at (row, first
 // Epilogue math on 4 consecutive columns of one row. v: accumulators; b / gm: bias / LayerScale gamma (zeros / ones when
 // absent); r: fp32 operand (residual / pos-embed); ax: 4 bf16 operands (GELU'). Outputs: of (fp32 out), oh (bf16 out),
 // oh2 (bf16 out2). Returns the value written to `out` (for the optional column-sum reduction).
-template <int EPI>
+template <int EPI, bool WANT_DGELU>
 __device__ __forceinline__ float4 epi_math4(float4 v, const float4 b, const float4 gm, const float4 r, const uint2 ax,
-                                            const float rs, const bool has_resid, const bool want_dgelu, float4& of,
-                                            uint2& oh, uint2& oh2) {
+                                            const float rs, float4& of, uint2& oh, uint2& oh2) {
     if constexpr (EpiTraits<EPI>::kBias) { v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
     if constexpr (EPI == EPI_STORE_BF16) {
         oh = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
     } else if constexpr (EPI == EPI_BIAS_GELU) {
         float g0, g1, g2, g3, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-        if (want_dgelu) {  // gelu'(pre) is only needed for backward
+        if constexpr (WANT_DGELU) {  // gelu'(pre) is only needed for backward
             gelu_pair<true>(v.x, v.y, g0, g1, d0, d1);
             gelu_pair<true>(v.z, v.w, g2, g3, d2, d3);
         } else {
@@ -137,7 +142,7 @@ __device__ __forceinline__ float4 epi_math4(float4 v, const float4 b, const floa
     } else if constexpr (EPI == EPI_RESID_F32) {
         oh2 = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
         v.x *= gm.x * rs; v.y *= gm.y * rs; v.z *= gm.z * rs; v.w *= gm.w * rs;
-        if (has_resid) { v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;  // zeros when there is no residual
         of = v;
     } else if constexpr (EPI == EPI_DGELU) {
         v.x *= bf16_lo(ax.x); v.y *= bf16_hi(ax.x); v.z *= bf16_lo(ax.y); v.w *= bf16_hi(ax.y);
@@ -197,6 +202,290 @@ __device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
 __device__ __forceinline__ int warp_colsum16_col(int lane) {
     return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
+
+// ----------------------------------------------------------------------------------------------------------------
+// Per-warp epilogue engine shared by the 1-CTA and the 2-CTA kernels. One instance per epilogue thread; `tile()` drains
+// this warp's [32 rows x BN/2 columns] slab of one accumulator stage.
+// ----------------------------------------------------------------------------------------------------------------
+template <int BN, int EPI> struct EpilogueWarp {
+    using T = EpiTraits<EPI>;
+    static constexpr int COLS_PER_WARP = BN / 2;
+    static constexpr int NCHUNK = COLS_PER_WARP / 16;
+    static constexpr int PF = T::kDepth < NCHUNK ? T::kDepth : NCHUNK;
+    static_assert(NCHUNK % PF == 0 && PF % 2 == 0, "prefetch ring must tile the chunk loop");
+    static constexpr int OUT_ESZ = T::kOutF32 ? 4 : 2;
+
+    const GemmArgs& g;
+    const int lane, quarter, half;
+    float* wvec;  // per-warp staging of this tile's bias / gamma columns: [bias COLS_PER_WARP | gamma COLS_PER_WARP]
+    uint32_t wvec_s;
+    bool has_bias, has_gamma, has_resid, want_out, vec_ok_static;
+
+    __device__ __forceinline__ EpilogueWarp(const GemmArgs& g_, float* svec, int ew, int warp, int lane_)
+        : g(g_), lane(lane_), quarter(warp & 3), half(ew >> 2) {
+        wvec = svec + ew * (2 * COLS_PER_WARP);
+        wvec_s = smem_u32(wvec);
+        has_bias = T::kBias && g.bias != nullptr;
+        has_gamma = T::kGamma && g.gamma != nullptr;
+        has_resid = T::kResid && g.resid != nullptr;
+        want_out = g.out != nullptr;
+        // 256-bit accesses need 32-byte aligned row segments (chunk starts are multiples of 16 columns)
+        auto aligned32 = [](const void* ptr, long long ld, int esz) {
+            return ptr == nullptr || (((reinterpret_cast<uintptr_t>(ptr) | (uintptr_t)(ld * esz)) & 31) == 0);
+        };
+        vec_ok_static = aligned32(g.out, g.ldo, OUT_ESZ) && aligned32(g.out2, g.ldo2, 2) &&
+                        (!T::kResid || aligned32(g.resid, g.ldr, 4)) && (!T::kAux || aligned32(g.aux, g.ldaux, 2)) &&
+                        ((g.so_h * OUT_ESZ) & 31) == 0 && ((g.so_b * OUT_ESZ) & 31) == 0;
+    }
+
+    // row state of tile (m_tile, n_tile, batch) for this lane
+    __device__ __forceinline__ void make_row(int m_tile, int n_tile, int batch, EpiRow& R, int& n0) const {
+        const long long ooff = (long long)(batch % g.nbatch_h) * g.so_h + (long long)(batch / g.nbatch_h) * g.so_b;
+        const long long row = (long long)m_tile * GEMM_BM + quarter * 32 + lane;
+        n0 = n_tile * BN + half * COLS_PER_WARP;
+        R.ok = row < g.M;
+        R.rs = 1.0f;
+        R.out2 = nullptr; R.resid = nullptr; R.aux = nullptr;
+        long long orow = row;  // output row
+        if constexpr (EPI == EPI_TOKENS_F32) {
+            const long long bimg = row / g.tok_n;
+            const int pp = static_cast<int>(row - bimg * g.tok_n);
+            orow = bimg * g.tok_N + g.tok_T + pp;
+            R.resid = g.resid + (long long)(g.tok_T + pp) * g.ldr + n0;  // pos_embed row
+        } else if constexpr (EPI == EPI_RESID_F32) {
+            if (has_resid) R.resid = g.resid + row * g.ldr + n0;
+            if (g.out2 != nullptr) R.out2 = reinterpret_cast<__nv_bfloat16*>(g.out2) + row * g.ldo2 + n0;
+            if (g.rowscale != nullptr && R.ok) R.rs = __ldg(g.rowscale + row / g.rows_per_sample);
+        } else if constexpr (EPI == EPI_BIAS_GELU) {
+            R.out2 = reinterpret_cast<__nv_bfloat16*>(g.out2) + row * g.ldo2 + n0;
+        } else if constexpr (EPI == EPI_DGELU) {
+            R.aux = g.aux + row * g.ldaux + n0;
+        }
+        R.out = want_out ? static_cast<void*>(reinterpret_cast<char*>(g.out) + (ooff + orow * g.ldo + n0) * OUT_ESZ)
+                         : nullptr;
+    }
+
+    // L2 prefetch of the accumulator-independent operand rows (residual / GELU') of a future tile
+    __device__ __forceinline__ void l2_prefetch(int m_tile, int n_tile, int batch) const {
+        if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_DGELU) {
+            if (g.dbg & 1) return;
+            EpiRow R;
+            int n0;
+            make_row(m_tile, n_tile, batch, R, n0);
+            const int nc = min(COLS_PER_WARP, g.N - n0) & ~7;  // 16-byte multiples for both element sizes
+            if (!R.ok || nc <= 0) return;
+            if constexpr (EPI == EPI_RESID_F32) {
+                if (R.resid != nullptr) prefetch_l2_bulk(R.resid, nc * 4);
+            } else {
+                prefetch_l2_bulk(R.aux, nc * 2);
+            }
+        }
+    }
+
+    // Drain this warp's slab of the accumulator stage at `taddr` (lane / column offsets of this warp already applied).
+    // `wait_acc()` blocks until the MMAs of the tile are complete; `release_acc()` is called once all TMEM reads of the
+    // stage are done (by all lanes; the callee elects).
+    // (the chunk math must be ONE basic block so that its 8 independent fp32x2 chains interleave: whether gelu' is
+    // wanted is therefore a template parameter, not a branch inside the math)
+    template <class WaitFn, class ReleaseFn>
+    __device__ __forceinline__ void tile(int m_tile, int n_tile, int batch, uint32_t taddr, WaitFn wait_acc,
+                                         ReleaseFn release_acc) {
+        if (EPI != EPI_BIAS_GELU || want_out) tile_impl<true>(m_tile, n_tile, batch, taddr, wait_acc, release_acc);
+        else tile_impl<false>(m_tile, n_tile, batch, taddr, wait_acc, release_acc);
+    }
+    template <bool WANT_DGELU, class WaitFn, class ReleaseFn>
+    __device__ __forceinline__ void tile_impl(int m_tile, int n_tile, int batch, uint32_t taddr, WaitFn wait_acc,
+                                              ReleaseFn release_acc) {
+        EpiRow R;
+        int n0;
+        make_row(m_tile, n_tile, batch, R, n0);
+        // stage bias / gamma of this warp's columns (zero / one padded beyond N)
+        if constexpr (T::kBias) {
+            if (lane * 4 < COLS_PER_WARP) {
+                const int col = n0 + lane * 4;
+                const float4 bv = (has_bias && col + 4 <= g.N) ? __ldg(reinterpret_cast<const float4*>(g.bias + col))
+                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(wvec + lane * 4) = bv;
+                if constexpr (T::kGamma) {
+                    const float4 gv = (has_gamma && col + 4 <= g.N)
+                                          ? __ldg(reinterpret_cast<const float4*>(g.gamma + col))
+                                          : make_float4(1.f, 1.f, 1.f, 1.f);
+                    *reinterpret_cast<float4*>(wvec + COLS_PER_WARP + lane * 4) = gv;
+                }
+            }
+            __syncwarp();
+        }
+
+        // operand ring: chunk c's residual / GELU' segment of this lane's row (vector path only)
+        uint32_t opq[PF][T::kOpWords];
+        auto chunk_is_vec = [&](int c) { return vec_ok_static && n0 + c * 16 + 16 <= g.N; };
+        auto fetch_chunk = [&](int c, uint32_t* dst) {
+            if (!R.ok || !chunk_is_vec(c)) return;
+            if (g.dbg & 4) return;
+            if constexpr (T::kResid) {
+                if (R.resid != nullptr) {
+                    if (g.dbg & 2) {
+                        ldg256_plain(R.resid + c * 16, dst);
+                        ldg256_plain(R.resid + c * 16 + 8, dst + 8);
+                    } else {
+                    ldg256(R.resid + c * 16, dst);
+                    ldg256(R.resid + c * 16 + 8, dst + 8);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) dst[i] = 0u;
+                }
+            } else if constexpr (T::kAux) {
+                ldg256(R.aux + c * 16, dst);
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < PF; ++j) fetch_chunk(j, opq[j]);  // in flight while we wait for the MMAs
+
+        wait_acc();
+        tc_fence_after_sync();
+        uint32_t racc[2][16];
+        tmem_ld_32x32b_x16(taddr, racc[0]);
+#pragma unroll 1
+        for (int c0 = 0; c0 < NCHUNK; c0 += PF) {
+#pragma unroll
+            for (int j = 0; j < PF; ++j) {
+                const int c = c0 + j;
+                const uint32_t* r = racc[j & 1];
+                tmem_ld_wait();
+                if (c + 1 < NCHUNK) {
+                    // the accumulator chunk is fetched one chunk ahead of its use
+                    tmem_ld_32x32b_x16(taddr + (c + 1) * 16, racc[(j + 1) & 1]);
+                } else {
+                    // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    release_acc();
+                }
+                const int col0 = n0 + c * 16;
+                if (col0 >= g.N) continue;  // (warp-uniform)
+                float cs[16];
+                if (chunk_is_vec(c)) {
+                    // ---- vector path: 16 columns, 256-bit global accesses
+                    uint32_t ho[8], ho2[8], fo[16];
+                    if constexpr (EPI == EPI_BIAS_GELU) {
+                        // all 8 fp32x2 pairs of the chunk in lock step (see gelu_pairs)
+                        float xv[16], gv[16], dv[16];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 b4 = lds_f4(wvec_s + (c * 16 + 4 * q) * 4);
+                            xv[4 * q] = __uint_as_float(r[4 * q]) + b4.x;
+                            xv[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
+                            xv[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
+                            xv[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
+                        }
+                        gelu_pairs<8, WANT_DGELU>(xv, gv, dv);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            ho2[i] = pack_bf16(gv[2 * i], gv[2 * i + 1]);
+                            if constexpr (WANT_DGELU) ho[i] = pack_bf16(dv[2 * i], dv[2 * i + 1]);
+                        }
+                    } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                     __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), r4 = b4;
+                        uint2 ax = make_uint2(0u, 0u);
+                        if constexpr (T::kBias) b4 = lds_f4(wvec_s + (c * 16 + 4 * q) * 4);
+                        if constexpr (T::kGamma) g4 = lds_f4(wvec_s + (COLS_PER_WARP + c * 16 + 4 * q) * 4);
+                        if constexpr (T::kResid)
+                            r4 = make_float4(__uint_as_float(opq[j][4 * q]), __uint_as_float(opq[j][4 * q + 1]),
+                                             __uint_as_float(opq[j][4 * q + 2]), __uint_as_float(opq[j][4 * q + 3]));
+                        if constexpr (T::kAux) ax = make_uint2(opq[j][2 * q], opq[j][2 * q + 1]);
+                        float4 of;
+                        uint2 oh, oh2;
+                        const float4 w = epi_math4<EPI, WANT_DGELU>(v, b4, g4, r4, ax, R.rs, of, oh, oh2);
+                        cs[4 * q] = w.x; cs[4 * q + 1] = w.y; cs[4 * q + 2] = w.z; cs[4 * q + 3] = w.w;
+                        if constexpr (T::kOutF32) {
+                            fo[4 * q] = __float_as_uint(of.x); fo[4 * q + 1] = __float_as_uint(of.y);
+                            fo[4 * q + 2] = __float_as_uint(of.z); fo[4 * q + 3] = __float_as_uint(of.w);
+                        } else {
+                            ho[2 * q] = oh.x; ho[2 * q + 1] = oh.y;
+                        }
+                        if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32) {
+                            ho2[2 * q] = oh2.x; ho2[2 * q + 1] = oh2.y;
+                        }
+                    }
+                    }
+                    if (R.ok && !(g.dbg & 8)) {
+                        if constexpr (EPI == EPI_ATOMIC_F32) {
+                            float* o = reinterpret_cast<float*>(R.out) + c * 16;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                red_add_v4_f32(o + 4 * q, __uint_as_float(fo[4 * q]), __uint_as_float(fo[4 * q + 1]),
+                                               __uint_as_float(fo[4 * q + 2]), __uint_as_float(fo[4 * q + 3]));
+                        } else if constexpr (T::kOutF32) {
+                            float* o = reinterpret_cast<float*>(R.out) + c * 16;
+                            stg256(o, fo);
+                            stg256(o + 8, fo + 8);
+                        } else {
+                            if (R.out != nullptr) stg256(reinterpret_cast<__nv_bfloat16*>(R.out) + c * 16, ho);
+                        }
+                        if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32) {
+                            if (R.out2 != nullptr) stg256(R.out2 + c * 16, ho2);
+                        }
+                    }
+                    if (c + PF < NCHUNK) fetch_chunk(c + PF, opq[j]);  // refill the ring slot just consumed
+                } else {
+                    // ---- 4-column path: N tail or unaligned pointers
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int cw = c * 16 + 4 * q;  // column within this warp's range
+                        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (n0 + cw + 4 <= g.N) {
+                            const float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                         __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), r4 = b4;
+                            uint2 ax = make_uint2(0u, 0u);
+                            if constexpr (T::kBias) b4 = lds_f4(wvec_s + cw * 4);
+                            if constexpr (T::kGamma) g4 = lds_f4(wvec_s + (COLS_PER_WARP + cw) * 4);
+                            if (R.ok) {
+                                if constexpr (T::kResid) {
+                                    if (R.resid != nullptr) r4 = *reinterpret_cast<const float4*>(R.resid + cw);
+                                }
+                                if constexpr (T::kAux) ax = *reinterpret_cast<const uint2*>(R.aux + cw);
+                            }
+                            float4 of;
+                            uint2 oh, oh2;
+                            w = epi_math4<EPI, WANT_DGELU>(v, b4, g4, r4, ax, R.rs, of, oh, oh2);
+                            if (R.ok) {
+                                if constexpr (EPI == EPI_ATOMIC_F32) {
+                                    red_add_v4_f32(reinterpret_cast<float*>(R.out) + cw, of.x, of.y, of.z, of.w);
+                                } else if constexpr (T::kOutF32) {
+                                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(R.out) + cw) = of;
+                                } else {
+                                    if (R.out != nullptr)
+                                        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(R.out) + cw) = oh;
+                                }
+                                if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32) {
+                                    if (R.out2 != nullptr) *reinterpret_cast<uint2*>(R.out2 + cw) = oh2;
+                                }
+                            }
+                        }
+                        cs[4 * q] = w.x; cs[4 * q + 1] = w.y; cs[4 * q + 2] = w.z; cs[4 * q + 3] = w.w;
+                    }
+                }
+                if constexpr (T::kColsum) {
+                    if (g.colsum != nullptr) {
+                        if (!R.ok) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) cs[i] = 0.f;
+                        }
+                        const float tot = warp_colsum16(cs, lane);
+                        const int col = col0 + warp_colsum16_col(lane);
+                        if ((lane & 1) == 0 && col < g.N) atomicAdd(g.colsum + col, tot);
+                    }
+                }
+            }
+        }
+    }
+};
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -355,245 +644,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp >= GEMM_EPI_WARP0) {
         // ===================== epilogue =====================
-        using T = EpiTraits<EPI>;
         const int ew = warp - GEMM_EPI_WARP0;
-        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-        const int half = ew >> 2;      // which half of the BN columns
-        constexpr int COLS_PER_WARP = BN / 2;
-        constexpr int NCHUNK = COLS_PER_WARP / 16;
-        constexpr int PF = T::kDepth < NCHUNK ? T::kDepth : NCHUNK;
-        static_assert(NCHUNK % PF == 0 && PF % 2 == 0, "prefetch ring must tile the chunk loop");
-        constexpr int OUT_ESZ = T::kOutF32 ? 4 : 2;
+        EpilogueWarp<BN, EPI> epi(g, svec, ew, warp, lane);
         int as = 0;
         uint32_t aphase = 0;
-        // per-warp staging of this tile's bias / gamma columns: [bias COLS_PER_WARP | gamma COLS_PER_WARP]
-        float* wvec = svec + ew * (2 * COLS_PER_WARP);
-        const uint32_t wvec_s = smem_u32(wvec);
-        const bool has_bias = T::kBias && g.bias != nullptr;
-        const bool has_gamma = T::kGamma && g.gamma != nullptr;
-        const bool has_resid = T::kResid && g.resid != nullptr;
-        const bool want_out = g.out != nullptr;
-        // 256-bit accesses need 32-byte aligned row segments (chunk starts are multiples of 16 columns)
-        auto aligned32 = [](const void* ptr, long long ld, int esz) {
-            return ptr == nullptr || (((reinterpret_cast<uintptr_t>(ptr) | (uintptr_t)(ld * esz)) & 31) == 0);
-        };
-        const bool vec_ok_static = aligned32(g.out, g.ldo, OUT_ESZ) && aligned32(g.out2, g.ldo2, 2) &&
-                                   (!T::kResid || aligned32(g.resid, g.ldr, 4)) &&
-                                   (!T::kAux || aligned32(g.aux, g.ldaux, 2)) &&
-                                   ((g.so_h * OUT_ESZ) & 31) == 0 && ((g.so_b * OUT_ESZ) & 31) == 0;
-
-        // row state of tile unit `un` for this lane
-        auto make_row = [&](int un, EpiRow& R, int& n0) {
-            const int n_tile = un % g.num_n_tiles;
+        auto decode = [&](int un, int& m_tile, int& n_tile, int& batch) {
+            n_tile = un % g.num_n_tiles;
             const int mb = (un / g.num_n_tiles) / g.splits;
-            const int m_tile = mb % g.num_m_tiles;
-            const int batch = mb / g.num_m_tiles;
-            const long long ooff = (long long)(batch % g.nbatch_h) * g.so_h + (long long)(batch / g.nbatch_h) * g.so_b;
-            const long long row = (long long)m_tile * GEMM_BM + quarter * 32 + lane;
-            n0 = n_tile * BN + half * COLS_PER_WARP;
-            R.ok = row < g.M;
-            R.rs = 1.0f;
-            R.out2 = nullptr; R.resid = nullptr; R.aux = nullptr;
-            long long orow = row;  // output row
-            if constexpr (EPI == EPI_TOKENS_F32) {
-                const long long bimg = row / g.tok_n;
-                const int pp = static_cast<int>(row - bimg * g.tok_n);
-                orow = bimg * g.tok_N + g.tok_T + pp;
-                R.resid = g.resid + (long long)(g.tok_T + pp) * g.ldr + n0;  // pos_embed row
-            } else if constexpr (EPI == EPI_RESID_F32) {
-                if (has_resid) R.resid = g.resid + row * g.ldr + n0;
-                if (g.out2 != nullptr) R.out2 = reinterpret_cast<__nv_bfloat16*>(g.out2) + row * g.ldo2 + n0;
-                if (g.rowscale != nullptr && R.ok) R.rs = __ldg(g.rowscale + row / g.rows_per_sample);
-            } else if constexpr (EPI == EPI_BIAS_GELU) {
-                R.out2 = reinterpret_cast<__nv_bfloat16*>(g.out2) + row * g.ldo2 + n0;
-            } else if constexpr (EPI == EPI_DGELU) {
-                R.aux = g.aux + row * g.ldaux + n0;
-            }
-            R.out = want_out ? static_cast<void*>(reinterpret_cast<char*>(g.out) + (ooff + orow * g.ldo + n0) * OUT_ESZ)
-                             : nullptr;
+            m_tile = mb % g.num_m_tiles;
+            batch = mb / g.num_m_tiles;
         };
-        // L2 prefetch of the accumulator-independent operand rows (residual / GELU') of a future tile
-        auto l2_prefetch_unit = [&](int un) {
-            if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_DGELU) {
-                if (un >= num_units) return;
-                EpiRow R;
-                int n0;
-                make_row(un, R, n0);
-                const int nc = min(COLS_PER_WARP, g.N - n0) & ~7;  // 16-byte multiples for both element sizes
-                if (!R.ok || nc <= 0) return;
-                if constexpr (EPI == EPI_RESID_F32) {
-                    if (R.resid != nullptr) prefetch_l2_bulk(R.resid, nc * 4);
-                } else {
-                    prefetch_l2_bulk(R.aux, nc * 2);
-                }
-            }
-        };
-        l2_prefetch_unit(blockIdx.x);
-
+        int m_tile, n_tile, batch;
+        decode(blockIdx.x, m_tile, n_tile, batch);
+        epi.l2_prefetch(m_tile, n_tile, batch);
         for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-            l2_prefetch_unit(u + gridDim.x);  // a whole tile of lead time
-            EpiRow R;
-            int n0;
-            make_row(u, R, n0);
-            const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN + half * COLS_PER_WARP;
-
-            // stage bias / gamma of this warp's columns (zero / one padded beyond N)
-            if constexpr (T::kBias) {
-                if (lane * 4 < COLS_PER_WARP) {
-                    const int col = n0 + lane * 4;
-                    const float4 bv = (has_bias && col + 4 <= g.N) ? __ldg(reinterpret_cast<const float4*>(g.bias + col))
-                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-                    *reinterpret_cast<float4*>(wvec + lane * 4) = bv;
-                    if constexpr (T::kGamma) {
-                        const float4 gv = (has_gamma && col + 4 <= g.N)
-                                              ? __ldg(reinterpret_cast<const float4*>(g.gamma + col))
-                                              : make_float4(1.f, 1.f, 1.f, 1.f);
-                        *reinterpret_cast<float4*>(wvec + COLS_PER_WARP + lane * 4) = gv;
-                    }
-                }
-                __syncwarp();
+            if (u + (int)gridDim.x < num_units) {  // a whole tile of lead time
+                decode(u + gridDim.x, m_tile, n_tile, batch);
+                epi.l2_prefetch(m_tile, n_tile, batch);
             }
-
-            // operand ring: chunk c's residual / GELU' segment of this lane's row (vector path only)
-            uint32_t opq[PF][T::kOpWords];
-            auto chunk_is_vec = [&](int c) { return vec_ok_static && n0 + c * 16 + 16 <= g.N; };
-            auto fetch_chunk = [&](int c, uint32_t* dst) {
-                if (!R.ok || !chunk_is_vec(c)) return;
-                if constexpr (T::kResid) {
-                    if (R.resid != nullptr) {
-                        ldg256(R.resid + c * 16, dst);
-                        ldg256(R.resid + c * 16 + 8, dst + 8);
-                    }
-                } else if constexpr (T::kAux) {
-                    ldg256(R.aux + c * 16, dst);
-                }
-            };
-#pragma unroll
-            for (int j = 0; j < PF; ++j) fetch_chunk(j, opq[j]);  // in flight while we wait for the MMAs
-
-            mbar_wait(&tfull_bar[as], aphase);
-            tc_fence_after_sync();
-            uint32_t racc[2][16];
-            tmem_ld_32x32b_x16(taddr, racc[0]);
-#pragma unroll 1
-            for (int c0 = 0; c0 < NCHUNK; c0 += PF) {
-#pragma unroll
-                for (int j = 0; j < PF; ++j) {
-                    const int c = c0 + j;
-                    const uint32_t* r = racc[j & 1];
-                    tmem_ld_wait();
-                    if (c + 1 < NCHUNK) {
-                        // the accumulator chunk is fetched one chunk ahead of its use
-                        tmem_ld_32x32b_x16(taddr + (c + 1) * 16, racc[(j + 1) & 1]);
-                    } else {
-                        // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty_bar[as]);
-                    }
-                    const int col0 = n0 + c * 16;
-                    if (col0 >= g.N) continue;  // (warp-uniform)
-                    float cs[16];
-                    if (chunk_is_vec(c)) {
-                        // ---- vector path: 16 columns, 256-bit global accesses
-                        uint32_t ho[8], ho2[8], fo[16];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                                         __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), r4 = b4;
-                            uint2 ax = make_uint2(0u, 0u);
-                            if constexpr (T::kBias) b4 = lds_f4(wvec_s + (c * 16 + 4 * q) * 4);
-                            if constexpr (T::kGamma) g4 = lds_f4(wvec_s + (COLS_PER_WARP + c * 16 + 4 * q) * 4);
-                            if constexpr (T::kResid)
-                                r4 = make_float4(__uint_as_float(opq[j][4 * q]), __uint_as_float(opq[j][4 * q + 1]),
-                                                 __uint_as_float(opq[j][4 * q + 2]), __uint_as_float(opq[j][4 * q + 3]));
-                            if constexpr (T::kAux) ax = make_uint2(opq[j][2 * q], opq[j][2 * q + 1]);
-                            float4 of;
-                            uint2 oh, oh2;
-                            const float4 w = epi_math4<EPI>(v, b4, g4, r4, ax, R.rs, R.resid != nullptr, want_out, of, oh, oh2);
-                            cs[4 * q] = w.x; cs[4 * q + 1] = w.y; cs[4 * q + 2] = w.z; cs[4 * q + 3] = w.w;
-                            if constexpr (T::kOutF32) {
-                                fo[4 * q] = __float_as_uint(of.x); fo[4 * q + 1] = __float_as_uint(of.y);
-                                fo[4 * q + 2] = __float_as_uint(of.z); fo[4 * q + 3] = __float_as_uint(of.w);
-                            } else {
-                                ho[2 * q] = oh.x; ho[2 * q + 1] = oh.y;
-                            }
-                            if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32) {
-                                ho2[2 * q] = oh2.x; ho2[2 * q + 1] = oh2.y;
-                            }
-                        }
-                        if (R.ok) {
-                            if constexpr (EPI == EPI_ATOMIC_F32) {
-                                float* o = reinterpret_cast<float*>(R.out) + c * 16;
-#pragma unroll
-                                for (int q = 0; q < 4; ++q)
-                                    red_add_v4_f32(o + 4 * q, __uint_as_float(fo[4 * q]), __uint_as_float(fo[4 * q + 1]),
-                                                   __uint_as_float(fo[4 * q + 2]), __uint_as_float(fo[4 * q + 3]));
-                            } else if constexpr (T::kOutF32) {
-                                float* o = reinterpret_cast<float*>(R.out) + c * 16;
-                                stg256(o, fo);
-                                stg256(o + 8, fo + 8);
-                            } else {
-                                if (R.out != nullptr) stg256(reinterpret_cast<__nv_bfloat16*>(R.out) + c * 16, ho);
-                            }
-                            if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32) {
-                                if (R.out2 != nullptr) stg256(R.out2 + c * 16, ho2);
-                            }
-                        }
-                        if (c + PF < NCHUNK) fetch_chunk(c + PF, opq[j]);  // refill the ring slot just consumed
-                    } else {
-                        // ---- 4-column path: N tail or unaligned pointers
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int cw = c * 16 + 4 * q;  // column within this warp's range
-                            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (n0 + cw + 4 <= g.N) {
-                                const float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                                             __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-                                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), r4 = b4;
-                                uint2 ax = make_uint2(0u, 0u);
-                                if constexpr (T::kBias) b4 = lds_f4(wvec_s + cw * 4);
-                                if constexpr (T::kGamma) g4 = lds_f4(wvec_s + (COLS_PER_WARP + cw) * 4);
-                                if (R.ok) {
-                                    if constexpr (T::kResid) {
-                                        if (R.resid != nullptr) r4 = *reinterpret_cast<const float4*>(R.resid + cw);
-                                    }
-                                    if constexpr (T::kAux) ax = *reinterpret_cast<const uint2*>(R.aux + cw);
-                                }
-                                float4 of;
-                                uint2 oh, oh2;
-                                w = epi_math4<EPI>(v, b4, g4, r4, ax, R.rs, R.resid != nullptr, want_out, of, oh, oh2);
-                                if (R.ok) {
-                                    if constexpr (EPI == EPI_ATOMIC_F32) {
-                                        red_add_v4_f32(reinterpret_cast<float*>(R.out) + cw, of.x, of.y, of.z, of.w);
-                                    } else if constexpr (T::kOutF32) {
-                                        *reinterpret_cast<float4*>(reinterpret_cast<float*>(R.out) + cw) = of;
-                                    } else {
-                                        if (R.out != nullptr)
-                                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(R.out) + cw) = oh;
-                                    }
-                                    if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_RESID_F32) {
-                                        if (R.out2 != nullptr) *reinterpret_cast<uint2*>(R.out2 + cw) = oh2;
-                                    }
-                                }
-                            }
-                            cs[4 * q] = w.x; cs[4 * q + 1] = w.y; cs[4 * q + 2] = w.z; cs[4 * q + 3] = w.w;
-                        }
-                    }
-                    if constexpr (T::kColsum) {
-                        if (g.colsum != nullptr) {
-                            if (!R.ok) {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) cs[i] = 0.f;
-                            }
-                            const float tot = warp_colsum16(cs, lane);
-                            const int col = col0 + warp_colsum16_col(lane);
-                            if ((lane & 1) == 0 && col < g.N) atomicAdd(g.colsum + col, tot);
-                        }
-                    }
-                }
-            }
+            decode(u, m_tile, n_tile, batch);
+            const uint32_t taddr =
+                tmem_base + (uint32_t((warp & 3) * 32) << 16) + as * BN + (ew >> 2) * (BN / 2);
+            epi.tile(m_tile, n_tile, batch, taddr, [&]() { mbar_wait(&tfull_bar[as], aphase); },
+                     [&]() { if (lane == 0) mbar_arrive(&tempty_bar[as]); });
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     }
