@@ -129,6 +129,16 @@ int vitk_prefix_tokens(const float* tok, const float* pos, float* out, int B, in
 /* Column sums of a bf16 matrix accumulated (+=) into fp32 out[N] (bias gradients: db = sum_rows dY). */
 int vitk_colsum_bf16(const void* x_bf16, long long ldx, long long rows, int N, float* out, void* stream);
 
+/* Multi-tensor SGD with momentum, torch.optim.SGD semantics with dampening 0 / no nesterov / no weight decay (the
+ * reference's 'sgd' optimiser, utils_network.py:119-126, stepped at utils_network.py:439-442), fused with the refresh
+ * of the bf16 GEMM-operand copy of each weight:  buf = momentum*buf + grad_scale*g ; p -= lr*buf ; w_bf16 = bf16(p).
+ *   table:     device array of { float* p; const float* g; float* buf; bf16* w_or_null; long long n; } (40 bytes each)
+ *   chunk_map: device array of int2 { tensor index, chunk index }, one thread block per vitk_sgd_chunk_elems() elements
+ *   first_step: momentum buffers are uninitialised (buf = grad_scale*g), as torch does on the first step. */
+int vitk_sgd_chunk_elems(void);
+int vitk_sgd_momentum_multi(const void* table, const void* chunk_map, int num_chunks, float lr, float momentum,
+                            float grad_scale, int first_step, void* stream);
+
 /* fp32 -> bf16 cast of n elements (weights, activations). n % 8 == 0 not required. */
 int vitk_cast_f32_bf16(const float* x, void* y_bf16, long long n, void* stream);
 

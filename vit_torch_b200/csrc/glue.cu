@@ -226,6 +226,61 @@ cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
 
 
 // ------------------------------------------------------------------------------------------------
+// Multi-tensor SGD with momentum (torch.optim.SGD semantics: dampening 0, no nesterov, no weight decay;
+// reference optimiser utils_network.py:119-126) fused with the refresh of the bf16 GEMM-operand copy of the weight:
+//   buf = momentum * buf + g * gscale ;  p -= lr * buf ;  w_bf16 = bf16(p)
+// One launch for the whole model: `tab` holds per-tensor pointers, `chunks` maps each thread block to
+// (tensor, first element). Reads 12 B, writes 8 (+2) B per parameter.
+// ------------------------------------------------------------------------------------------------
+struct SgdTensor {
+    float* p;
+    const float* g;
+    float* buf;
+    __nv_bfloat16* w;  // may be null
+    long long n;
+};
+constexpr int SGD_CHUNK = 16384;  // elements per thread block
+
+__global__ void __launch_bounds__(256)
+sgd_momentum_multi_kernel(const SgdTensor* __restrict__ tab, const int2* __restrict__ chunks, float lr, float momentum,
+                          float gscale, int first_step) {
+    const int2 ck = chunks[blockIdx.x];  // x = tensor index, y = chunk index within the tensor
+    const SgdTensor t = tab[ck.x];
+    const long long base = (long long)ck.y * SGD_CHUNK;
+    const long long end = min(base + SGD_CHUNK, t.n);
+    const bool vec = ((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g) |
+                       reinterpret_cast<uintptr_t>(t.buf)) & 15) == 0 &&
+                     (t.w == nullptr || (reinterpret_cast<uintptr_t>(t.w) & 7) == 0);
+    if (vec) {
+        const long long end4 = base + ((end - base) & ~3LL);
+        for (long long i = base + threadIdx.x * 4; i < end4; i += 256 * 4) {
+            const float4 g = *reinterpret_cast<const float4*>(t.g + i);
+            float4 p = *reinterpret_cast<const float4*>(t.p + i);
+            float4 b = first_step ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(t.buf + i);
+            b.x = fmaf(momentum, b.x, g.x * gscale); b.y = fmaf(momentum, b.y, g.y * gscale);
+            b.z = fmaf(momentum, b.z, g.z * gscale); b.w = fmaf(momentum, b.w, g.w * gscale);
+            p.x = fmaf(-lr, b.x, p.x); p.y = fmaf(-lr, b.y, p.y); p.z = fmaf(-lr, b.z, p.z); p.w = fmaf(-lr, b.w, p.w);
+            *reinterpret_cast<float4*>(t.buf + i) = b;
+            *reinterpret_cast<float4*>(t.p + i) = p;
+            if (t.w != nullptr) *reinterpret_cast<uint2*>(t.w + i) = make_uint2(pack_bf16(p.x, p.y), pack_bf16(p.z, p.w));
+        }
+        for (long long i = end4 + threadIdx.x; i < end; i += 256) {
+            const float b = fmaf(momentum, first_step ? 0.f : t.buf[i], t.g[i] * gscale);
+            const float p = fmaf(-lr, b, t.p[i]);
+            t.buf[i] = b; t.p[i] = p;
+            if (t.w != nullptr) t.w[i] = __float2bfloat16_rn(p);
+        }
+    } else {
+        for (long long i = base + threadIdx.x; i < end; i += 256) {
+            const float b = fmaf(momentum, first_step ? 0.f : t.buf[i], t.g[i] * gscale);
+            const float p = fmaf(-lr, b, t.p[i]);
+            t.buf[i] = b; t.p[i] = p;
+            if (t.w != nullptr) t.w[i] = __float2bfloat16_rn(p);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // fp32 column sums with a row stride: out[c] += sum_r x[r*ldx + c]   (d_pos = sum_b dX[b], d_cls)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -523,6 +578,19 @@ extern "C" int vitk_prefix_tokens(const float* tok, const float* pos, float* out
     if (B <= 0 || T <= 0 || D <= 0 || !tok || !pos || !out) return VITK_ERR_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     prefix_tokens_kernel<<<ew_grid((long long)B * T * D), 256, 0, st>>>(tok, pos, out, B, T, tokens_per_image, D);
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
+extern "C" int vitk_sgd_chunk_elems(void) { return SGD_CHUNK; }
+
+extern "C" int vitk_sgd_momentum_multi(const void* table, const void* chunk_map, int num_chunks, float lr,
+                                       float momentum, float grad_scale, int first_step, void* stream) {
+    if (num_chunks < 0 || (num_chunks > 0 && (!table || !chunk_map))) return VITK_ERR_ARG;
+    if (num_chunks == 0) return VITK_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    sgd_momentum_multi_kernel<<<num_chunks, 256, 0, st>>>(reinterpret_cast<const SgdTensor*>(table),
+                                                          reinterpret_cast<const int2*>(chunk_map), lr, momentum,
+                                                          grad_scale, first_step);
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
 }
 

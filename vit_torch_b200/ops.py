@@ -378,3 +378,16 @@ for _name in ("gemm", "gemm_batched", "layernorm_fwd", "layernorm_bwd", "layerno
               "colsum_accum", "colsum_f32_accum", "colsum_prod_accum", "cast_bf16", "attn_fwd", "attn_bwd", "scale_cast",
               "patchify", "prefix_tokens", "th_mix_fwd", "th_mix_bwd", "class_attn_fwd", "class_attn_bwd"):
     globals()[_name] = _timed(globals()[_name])
+
+
+def sgd_momentum_multi(table, chunk_map, num_chunks, lr, momentum, grad_scale=1.0, first_step=False):
+    """One launch of the fused multi-tensor SGD(momentum) + bf16 weight refresh. See vitk_sgd_momentum_multi."""
+    global launch_count
+    _need_cuda(table, chunk_map)
+    lib = _lib.load()
+    check(lib.vitk_sgd_momentum_multi(ptr(table), ptr(chunk_map), int(num_chunks), float(lr), float(momentum),
+                                      float(grad_scale), int(bool(first_step)), _stream()), "vitk_sgd_momentum_multi")
+    launch_count += 1
+
+
+sgd_momentum_multi = _timed(sgd_momentum_multi) if "_timed" in globals() else sgd_momentum_multi

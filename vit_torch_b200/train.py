@@ -16,11 +16,92 @@ def reset_parameters_like_zoo(m: nn.Module) -> None:
         m.reset_parameters()
 
 
+class FusedSGD(torch.optim.Optimizer):
+    """torch.optim.SGD(params, lr, momentum) -- the reference's 'sgd' entry (utils_network.py:119-126) -- as ONE
+    multi-tensor kernel per step that also refreshes the bf16 GEMM-operand copies of the weights
+    (vitk_sgd_momentum_multi). Same constructor keywords, `param_groups[i]['lr']` stays the knob LambdaLR turns
+    (utils_network.py:218-225), state_dict() keeps torch's `momentum_buffer` naming. dampening / nesterov /
+    weight_decay other than the reference's zeros raise."""
+
+    def __init__(self, params, lr=1e-3, momentum=0.0, dampening=0, weight_decay=0, nesterov=False):
+        if dampening != 0 or weight_decay != 0 or nesterov:
+            raise NotImplementedError("FusedSGD implements the reference configuration: plain momentum SGD")
+        super().__init__(params, dict(lr=lr, momentum=momentum, dampening=0, weight_decay=0, nesterov=False))
+        self._plan = {}       # group index -> cached launch plan
+        self._pinned = []     # rotating pinned staging buffers for the pointer tables
+        self._slot = 0
+
+    def _build_plan(self, ps, dev):
+        import numpy as np
+
+        from . import ops
+        chunk = ops._lib.load().vitk_sgd_chunk_elems()
+        rows, cmap, ws = [], [], []
+        for t, p in enumerate(ps):
+            st = self.state[p]
+            if "momentum_buffer" not in st:  # torch: buf = g on the first step == momentum * 0 + g
+                st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            w = self._bf16_copy(p)
+            ws.append(w)
+            rows.append([p.data_ptr(), 0, st["momentum_buffer"].data_ptr(), w.data_ptr() if w is not None else 0,
+                         p.numel()])
+            cmap += [(t, c) for c in range((p.numel() + chunk - 1) // chunk)]
+        table = np.asarray(rows, dtype=np.int64).reshape(-1, 5)
+        cmap_dev = torch.tensor(cmap, dtype=torch.int32).view(-1, 2).to(dev)
+        return dict(ids=[id(p) for p in ps], table=table, cmap=cmap_dev, nchunks=len(cmap), ws=ws,
+                    dev_table=torch.empty((len(ps), 5), dtype=torch.int64, device=dev))
+
+    @staticmethod
+    def _bf16_copy(p):
+        """The live bf16 GEMM-operand copy of `p` held by functional.bf16_weight's cache, or None."""
+        from . import functional
+        ent = functional._wcache.get(id(p))
+        if ent is not None and ent[0]() is p and ent[1] == p._version and ent[2] == p.data_ptr():
+            return ent[3]
+        return None
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        from . import ops
+        loss = closure() if closure is not None else None
+        for gi, group in enumerate(self.param_groups):
+            ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            for p in ps:
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                    raise ops._lib.VitkError("FusedSGD needs contiguous fp32 CUDA parameters (no CPU fallback)")
+            plan = self._plan.get(gi)
+            if (plan is None or plan["ids"] != [id(p) for p in ps]
+                    or any(self._bf16_copy(p) is not w for p, w in zip(ps, plan["ws"]))):
+                plan = self._plan[gi] = self._build_plan(ps, ps[0].device)
+            tab = plan["table"]
+            for t, p in enumerate(ps):
+                g = p.grad
+                if not (g.is_contiguous() and g.dtype == torch.float32):
+                    g = p.grad = g.contiguous().float()
+                tab[t, 0] = p.data_ptr()
+                tab[t, 1] = g.data_ptr()
+            if len(self._pinned) < 8:
+                self._pinned.append(torch.empty((len(ps), 5), dtype=torch.int64).pin_memory())
+            pin = self._pinned[self._slot % len(self._pinned)]
+            self._slot += 1
+            if pin.shape != (len(ps), 5):
+                pin = self._pinned[(self._slot - 1) % len(self._pinned)] = torch.empty((len(ps), 5),
+                                                                                        dtype=torch.int64).pin_memory()
+            pin.numpy()[...] = tab
+            plan["dev_table"].copy_(pin, non_blocking=True)
+            ops.sgd_momentum_multi(plan["dev_table"], plan["cmap"], plan["nchunks"], group["lr"], group["momentum"],
+                                   1.0, False)
+        return loss
+
+
 class Trainer:
-    def __init__(self, model: nn.Module, lr: float = 1e-3, momentum: float = 0.9, reducer=None):
+    def __init__(self, model: nn.Module, lr: float = 1e-3, momentum: float = 0.9, reducer=None, fused_opt: bool = True):
         self.model = model
         self.reducer = reducer
-        self.opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=lr, momentum=momentum)
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.opt = (FusedSGD if fused_opt else torch.optim.SGD)(params, lr=lr, momentum=momentum)
         self.extra_launches_per_step = 0
 
     def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
