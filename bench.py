@@ -47,6 +47,27 @@ def gemm_flops_per_image(N, D, L, P, C=3):
     return 3 * lin + 2 * (2 * n * C * P * P * D)
 
 
+def gemm_bytes_per_image(N, D, L, P, C=3):
+    """Algorithmic DRAM bytes of the GEMM launches per image per train step (bf16 operands and saved activations, fp32
+    residual stream and weight gradients; weights counted once per launch, amortised over the batch elsewhere)."""
+    a = N * D  # elements of one [N, D] activation
+    fwd = (2 * a + 6 * a) + (2 * a + 4 * a + 4 * a) + (2 * a + 8 * a + 8 * a) + (8 * a + 4 * a + 4 * a)
+    dgrad = (2 * a + 8 * a + 8 * a) + (8 * a + 2 * a) + (2 * a + 2 * a) + (6 * a + 2 * a)
+    wgrad = (2 * a + 8 * a) + (8 * a + 2 * a) + (2 * a + 2 * a) + (6 * a + 2 * a)
+    return L * (fwd + dgrad + wgrad)
+
+
+def measured_gemm_traffic():
+    """Per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the GEMM launches of one step, from the
+    committed ncu capture of this same command (profiles/r01_gemm_traffic.json, scripts/gpu_profile.sh)."""
+    path = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["traffic_per_launch_bytes"])
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -68,7 +89,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "25"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -149,7 +170,7 @@ def cpu_baseline(args):
     ots.step(model, opt, x, y)
     t0 = time.perf_counter()
     steps = 0
-    while steps < 3 or (time.perf_counter() - t0 < 10 and steps < 8):
+    while steps < 3 or (time.perf_counter() - t0 < 12 and steps < 40):
         ots.step(model, opt, x, y)
         steps += 1
     dt = time.perf_counter() - t0
@@ -273,7 +294,10 @@ def main():
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_sustained"], "frac_of_burst_peak": achieved / pk["bf16_burst"],
                 "peak_source": pk["source"] + " (sustained cuBLAS bf16, kernel timed inside a long step)",
-                "traffic": None, "launches": gemm_launches, "avg_launch_us": gemm_ms * 1e3 / max(gemm_launches, 1),
+                "traffic": measured_gemm_traffic() if (args.workload == "dino_vitb16" and bs == 128) else None,
+                "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_gemm_traffic.json)",
+                "algorithmic_bytes_per_launch": gemm_bytes_per_image(N, D, L, P) * bs * args.steps / max(gemm_launches, 1),
+                "launches": gemm_launches, "avg_launch_us": gemm_ms * 1e3 / max(gemm_launches, 1),
                 "share_of_step": gemm_ms / (ms if ms > 0 else 1.0)}
 
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
