@@ -2,6 +2,7 @@
 // reductions), bias-gradient column sums, dtype casts. All HBM-roofline kernels: no smem staging needed because
 // every element is touched once; grids are multiples of the SM count with grid-stride loops.
 #include "common.cuh"
+#include <stdlib.h>
 #include "tmap.cuh"
 #include "../../include/vitk.h"
 
@@ -176,6 +177,171 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long lo
             a += part[k * 3 * Dp + c];
             bsum += part[k * 3 * Dp + Dp + c];
             xsum += part[k * 3 * Dp + 2 * Dp + c];
+        }
+        if (dweight != nullptr) atomicAdd(dweight + c, a);
+        if (dbias != nullptr) atomicAdd(dbias + c, bsum);
+        if (dxsum != nullptr) atomicAdd(dxsum + c, xsum);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward, TMA-staged variant for large row counts. Same math and outputs as ln_bwd_kernel.
+// ncu on ln_bwd_kernel (25216 x 768): 4.08 TB/s = 62 % of HBM peak with 70 % of the samples on the long scoreboard --
+// a warp cannot have the next row's loads in flight while it reduces the current one. Here a producer thread streams
+// whole rows (x fp32 | dres fp32 | dy) into a shared-memory ring with 1-D bulk async copies (cp.async.bulk, completion
+// counted on an mbarrier per stage), so LNR_STAGES rows per SM are always in flight; eight consumer warps take the
+// rows round-robin, keep xhat / dy*w of the row and the dweight / dbias / column-sum partials in registers, and store
+// dx (fp32) and its bf16 copy straight from registers.
+// ------------------------------------------------------------------------------------------------
+constexpr int LNR_CONSUMERS = 8;
+constexpr int LNR_THREADS = (LNR_CONSUMERS + 1) * 32;
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int MAXC, bool DY_F32>
+__global__ void __launch_bounds__(LNR_THREADS, 1)
+ln_bwd_ring_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long long x_stride,
+                   const float* __restrict__ w, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                   const float* __restrict__ dres, float* __restrict__ dx, long long dx_stride,
+                   __nv_bfloat16* __restrict__ dx_bf16, const float* __restrict__ colscale, float* __restrict__ dweight,
+                   float* __restrict__ dbias, float* __restrict__ dxsum, long long rows, int D, int stages) {
+    constexpr int Dp = MAXC * 128;
+    extern __shared__ __align__(128) uint8_t lnr_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t x_bytes = D * 4, r_bytes = (dres != nullptr) ? D * 4 : 0, dy_bytes = D * (DY_F32 ? 4 : 2);
+    const uint32_t stage_bytes = ((x_bytes + D * 4 + D * (DY_F32 ? 4 : 2)) + 127) & ~127u;
+    uint8_t* ring = lnr_smem;
+    float* sw = reinterpret_cast<float*>(lnr_smem + (size_t)stages * stage_bytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(sw + Dp);
+    uint64_t* empty = full + stages;
+    for (int c = threadIdx.x; c < Dp; c += LNR_THREADS) sw[c] = (c < D) ? w[c] : 0.f;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < stages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    // rows of this block: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const long long nloc = (rows - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    float4 aw[MAXC], ab[MAXC], ax[MAXC];
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) aw[i] = ab[i] = ax[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    if (warp == LNR_CONSUMERS) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (long long k = 0; k < nloc; ++k) {
+                const long long row = blockIdx.x + k * gridDim.x;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* st = ring + (size_t)s * stage_bytes;
+                mbar_expect_tx(&full[s], x_bytes + r_bytes + dy_bytes);
+                bulk_g2s(st, x + row * x_stride, x_bytes, &full[s]);
+                if (r_bytes) bulk_g2s(st + x_bytes, dres + row * dx_stride, r_bytes, &full[s]);
+                bulk_g2s(st + 2 * x_bytes, reinterpret_cast<const uint8_t*>(dy_) + (size_t)row * dy_bytes, dy_bytes,
+                         &full[s]);
+                if (++s == stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // ===================== consumers =====================
+        const float inv_d = 1.0f / static_cast<float>(D);
+        for (long long k = warp; k < nloc; k += LNR_CONSUMERS) {
+            const long long row = blockIdx.x + k * gridDim.x;
+            const int s = static_cast<int>(k % stages);
+            const uint32_t ph = static_cast<uint32_t>((k / stages) & 1);
+            const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
+            mbar_wait(&full[s], ph);
+            const uint8_t* st = ring + (size_t)s * stage_bytes;
+            const float* sx = reinterpret_cast<const float*>(st);
+            const float* sr = reinterpret_cast<const float*>(st + x_bytes);
+            float4 xh[MAXC], gv[MAXC];
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < MAXC; ++i) {
+                const int c = (i * 32 + lane) * 4;
+                if (c < D) {
+                    const float4 xv = *reinterpret_cast<const float4*>(sx + c);
+                    float4 dv;
+                    if constexpr (DY_F32) {
+                        dv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(st + 2 * x_bytes) + c);
+                    } else {
+                        const uint2 t = *reinterpret_cast<const uint2*>(
+                            reinterpret_cast<const __nv_bfloat16*>(st + 2 * x_bytes) + c);
+                        dv = make_float4(bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y));
+                    }
+                    const float4 wv = *reinterpret_cast<const float4*>(sw + c);
+                    xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd,
+                                        (xv.w - mean) * rstd);
+                    aw[i].x += dv.x * xh[i].x; aw[i].y += dv.y * xh[i].y; aw[i].z += dv.z * xh[i].z; aw[i].w += dv.w * xh[i].w;
+                    ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
+                    gv[i] = make_float4(dv.x * wv.x, dv.y * wv.y, dv.z * wv.z, dv.w * wv.w);
+                    s1 += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
+                    s2 += (gv[i].x * xh[i].x + gv[i].y * xh[i].y) + (gv[i].z * xh[i].z + gv[i].w * xh[i].w);
+                } else {
+                    xh[i] = gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
+            float4 rv[MAXC];
+#pragma unroll
+            for (int i = 0; i < MAXC; ++i) {
+                const int c = (i * 32 + lane) * 4;
+                rv[i] = (r_bytes && c < D) ? *reinterpret_cast<const float4*>(sr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            // every shared-memory read of the stage is done: hand it back to the producer before the global stores
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+#pragma unroll
+            for (int i = 0; i < MAXC; ++i) {
+                const int c = (i * 32 + lane) * 4;
+                if (c < D) {
+                    float4 o = make_float4(rstd * (gv[i].x - c1 - xh[i].x * c2) + rv[i].x,
+                                           rstd * (gv[i].y - c1 - xh[i].y * c2) + rv[i].y,
+                                           rstd * (gv[i].z - c1 - xh[i].z * c2) + rv[i].z,
+                                           rstd * (gv[i].w - c1 - xh[i].w * c2) + rv[i].w);
+                    if (dx != nullptr) *reinterpret_cast<float4*>(dx + row * dx_stride + c) = o;
+                    if (dx_bf16 != nullptr) {
+                        if (colscale != nullptr) {
+                            const float4 cs = __ldg(reinterpret_cast<const float4*>(colscale + c));
+                            o.x *= cs.x; o.y *= cs.y; o.z *= cs.z; o.w *= cs.w;
+                        }
+                        *reinterpret_cast<uint2*>(dx_bf16 + row * D + c) =
+                            make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+                        ax[i].x += o.x; ax[i].y += o.y; ax[i].z += o.z; ax[i].w += o.w;
+                    }
+                }
+            }
+        }
+    }
+    // block reduction of the per-warp register partials through the (now idle) ring, one atomic per column per block
+    __syncthreads();
+    float* part = reinterpret_cast<float*>(ring);  // [LNR_CONSUMERS][3][Dp]
+    if (warp < LNR_CONSUMERS) {
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            *reinterpret_cast<float4*>(part + (warp * 3 + 0) * Dp + c) = aw[i];
+            *reinterpret_cast<float4*>(part + (warp * 3 + 1) * Dp + c) = ab[i];
+            *reinterpret_cast<float4*>(part + (warp * 3 + 2) * Dp + c) = ax[i];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += LNR_THREADS) {
+        float a = 0.f, bsum = 0.f, xsum = 0.f;
+#pragma unroll
+        for (int k = 0; k < LNR_CONSUMERS; ++k) {
+            a += part[(k * 3 + 0) * Dp + c];
+            bsum += part[(k * 3 + 1) * Dp + c];
+            xsum += part[(k * 3 + 2) * Dp + c];
         }
         if (dweight != nullptr) atomicAdd(dweight + c, a);
         if (dbias != nullptr) atomicAdd(dbias + c, bsum);
@@ -422,9 +588,9 @@ static int ln_fwd_impl(const float* x, long long x_stride, const float* weight, 
     if (rows <= 0 || D <= 0 || (D % 4) != 0 || D > 1024 || (x_stride % 4) != 0) return VITK_ERR_ARG;
     if (!x || !weight || !bias || (!y_bf16 && !y_f32) || !mean || !rstd) return VITK_ERR_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int grid = ln_grid(rows);
     auto y = reinterpret_cast<__nv_bfloat16*>(y_bf16);
     const int chunks = (D + 127) / 128;
+    const int grid = ln_grid(rows);
 #define VITK_LN_FWD(C) \
     ln_fwd_kernel<C><<<grid, LN_WARPS * 32, 0, st>>>(x, x_stride, weight, bias, y, y_f32, mean, rstd, rows, D, eps)
     if (chunks <= 2) VITK_LN_FWD(2);
@@ -454,11 +620,54 @@ static int ln_bwd_impl(const void* dy, int dy_is_f32, const float* x, long long 
         return VITK_ERR_ARG;
     if (!dy || !x || !weight || !mean || !rstd) return VITK_ERR_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    auto dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+    const int chunks = (D + 127) / 128;
+    // large problems: TMA-staged ring kernel (bulk copies need 16-byte row segments: D % 8 == 0 covers bf16 rows)
+    static int ring_off = -1;
+    if (ring_off < 0) { const char* e = getenv("VITK_LN_RING"); ring_off = (e != nullptr && e[0] == '0') ? 1 : 0; }
+    if (!ring_off && rows >= 4096 && (D % 8) == 0 && D >= 128 &&
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dres)) & 15) == 0) {
+        const int cpad = chunks <= 2 ? 2 : chunks <= 3 ? 3 : chunks <= 6 ? 6 : 8;
+        const int Dp = cpad * 128;
+        const unsigned stage_bytes = ((unsigned)(D * 4 + D * 4 + D * (dy_is_f32 ? 4 : 2)) + 127u) & ~127u;
+        const long long fixed = (long long)Dp * 4 + 2 * 64 * 8 + 256;
+        int stages = (int)((220 * 1024 - fixed) / stage_bytes);
+        if (stages > 32) stages = 32;
+        const long long part_bytes = (long long)LNR_CONSUMERS * 3 * Dp * 4;
+        while ((long long)stages * stage_bytes < part_bytes) ++stages;  // the ring doubles as the reduction scratch
+        const int smem = (int)((long long)stages * stage_bytes + Dp * 4 + 2 * stages * 8 + 128);
+        if (smem <= 227 * 1024 && stages >= 4) {
+            const int grid = (int)(rows < sm_count() ? rows : sm_count());
+#define VITK_LN_RING_ONE(C, F)                                                                                        \
+    do {                                                                                                              \
+        static int attr_smem = 0;                                                                                     \
+        if (attr_smem < smem) {                                                                                       \
+            if (cudaFuncSetAttribute(ln_bwd_ring_kernel<C, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=  \
+                cudaSuccess)                                                                                          \
+                return VITK_ERR_CUDA;                                                                                 \
+            attr_smem = smem;                                                                                         \
+        }                                                                                                             \
+        ln_bwd_ring_kernel<C, F><<<grid, LNR_THREADS, smem, st>>>(dy, x, x_stride, weight, mean, rstd, dres, dx,      \
+                                                                  dx_stride, dxb, colscale, dweight, dbias, dxsum,   \
+                                                                  rows, D, stages);                                   \
+    } while (0)
+#define VITK_LN_RING(C)                           \
+    do {                                          \
+        if (dy_is_f32) VITK_LN_RING_ONE(C, true); \
+        else VITK_LN_RING_ONE(C, false);          \
+    } while (0)
+            if (cpad == 2) VITK_LN_RING(2);
+            else if (cpad == 3) VITK_LN_RING(3);
+            else if (cpad == 6) VITK_LN_RING(6);
+            else VITK_LN_RING(8);
+#undef VITK_LN_RING
+#undef VITK_LN_RING_ONE
+            return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+        }
+    }
     long long need = (rows + LN_WARPS - 1) / LN_WARPS;
     const long long cap = (long long)sm_count() * 2;
     const int grid = (int)(need < cap ? need : cap);
-    auto dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
-    const int chunks = (D + 127) / 128;
 #define VITK_LN_BWD_ONE(C, F)                                                                                        \
     do {                                                                                                             \
         constexpr int smem = (1 + 3 * LN_WARPS) * (C) * 128 * 4;                                                     \
