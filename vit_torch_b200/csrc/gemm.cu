@@ -28,8 +28,9 @@ static int choose_splits(int tiles, int num_kblocks, int sms) {
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmO2,
+                       const GemmArgs& g, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN, EPI>;
     auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI>;
     static bool attr_set = false;  // benign race: idempotent
     if (!attr_set) {
@@ -39,7 +40,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     }
     const int units = g.num_m_tiles * g.num_n_tiles * g.splits * g.nbatch_h * g.nbatch_b;
     const int grid = units < sm_count() ? units : sm_count();
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmO2, g);
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
 }
 
@@ -61,8 +62,9 @@ static bool use_2cta() {
 }
 
 template <bool A_MN, bool B_MN, int EPI>
-static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
-    using Cfg = Gemm2Cfg;
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmO2,
+                        const GemmArgs& g, cudaStream_t stream) {
+    using Cfg = Gemm2Cfg<EPI>;
     auto kern = gemm2_bf16_kernel<A_MN, B_MN, EPI>;
     static bool attr_set = false;  // benign race: idempotent
     if (!attr_set) {
@@ -72,14 +74,15 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
     }
     const int units = ((g.num_m_tiles + 1) / 2) * g.num_n_tiles * g.splits;
     const int clusters = units < max_clusters() ? units : max_clusters();
-    kern<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);  // static __cluster_dims__(2,1,1)
+    kern<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmO2, g);  // static __cluster_dims__(2,1,1)
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
 }
 
-static int dispatch_gemm2(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g,
-                          cudaStream_t s) {
-#define VITK_CASE2(AM, BM_, E)                                 \
-    if (a_mn == (AM) && b_mn == (BM_) && epi == (E)) return launch_gemm2<(AM) != 0, (BM_) != 0, (E)>(tmA, tmB, g, s);
+static int dispatch_gemm2(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                          const CUtensorMap& tmO, const CUtensorMap& tmO2, const GemmArgs& g, cudaStream_t s) {
+#define VITK_CASE2(AM, BM_, E)                       \
+    if (a_mn == (AM) && b_mn == (BM_) && epi == (E)) \
+        return launch_gemm2<(AM) != 0, (BM_) != 0, (E)>(tmA, tmB, tmO, tmO2, g, s);
     VITK_CASE2(0, 0, EPI_STORE_BF16)
     VITK_CASE2(0, 0, EPI_BIAS_GELU)
     VITK_CASE2(0, 0, EPI_RESID_F32)
@@ -96,10 +99,11 @@ static bool gemm2_supported(int a_mn, int b_mn, int epi) {
 }
 
 template <int BN>
-static int dispatch_gemm(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g,
-                         cudaStream_t s) {
-#define VITK_CASE(AM, BM_, E)                                  \
-    if (a_mn == (AM) && b_mn == (BM_) && epi == (E)) return launch_gemm<BN, (AM) != 0, (BM_) != 0, (E)>(tmA, tmB, g, s);
+static int dispatch_gemm(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                         const CUtensorMap& tmO, const CUtensorMap& tmO2, const GemmArgs& g, cudaStream_t s) {
+#define VITK_CASE(AM, BM_, E)                        \
+    if (a_mn == (AM) && b_mn == (BM_) && epi == (E)) \
+        return launch_gemm<BN, (AM) != 0, (BM_) != 0, (E)>(tmA, tmB, tmO, tmO2, g, s);
     // forward Linear: activations K-major, weight [N,K] K-major
     VITK_CASE(0, 0, EPI_STORE_BF16)
     VITK_CASE(0, 0, EPI_BIAS_GELU)
@@ -221,10 +225,42 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
     if (rc) return VITK_ERR_TMAP;
     }
 
+    // outputs through TMA stores (non-batched, 16-byte aligned rows): [32 rows x 64 B] boxes per epilogue warp
+    CUtensorMap tmO, tmO2;
+    memset(&tmO, 0, sizeof(tmO));
+    memset(&tmO2, 0, sizeof(tmO2));
+    g.tma_out = 0;
+    {
+        static int tma_off = -1;
+        if (tma_off < 0) { const char* e = getenv("VITK_GEMM_TMA_STORE"); tma_off = (e != nullptr && e[0] == '0') ? 1 : 0; }
+        const bool f32out = (epilogue == EPI_RESID_F32 || epilogue == EPI_STORE_F32);
+        const int esz = f32out ? 4 : 2;
+        auto ok16 = [](const void* p_, long long ld, int es) {
+            return p_ != nullptr && ((reinterpret_cast<uintptr_t>(p_) | (uintptr_t)(ld * es)) & 15) == 0;
+        };
+        bool use = !tma_off && nh * nb == 1 &&
+                   (epilogue == EPI_STORE_BF16 || epilogue == EPI_BIAS_GELU || epilogue == EPI_RESID_F32 ||
+                    epilogue == EPI_DGELU || epilogue == EPI_STORE_F32);
+        if (use) {
+            // BIAS_GELU: `out` (gelu') is optional, `out2` (gelu) is the mandatory bf16 output
+            if (epilogue == EPI_BIAS_GELU) use = ok16(out2, ldo2, 2) && (out == nullptr || ok16(out, ldo, 2));
+            else use = ok16(out, ldo, esz);
+        }
+        if (use) {
+            if (epilogue == EPI_BIAS_GELU) {
+                if (out != nullptr && make_tmap_2d_store(&tmO, out, 2, (uint64_t)Nepi, (uint64_t)M, (uint64_t)ldo, 32))
+                    return VITK_ERR_TMAP;
+                if (make_tmap_2d_store(&tmO2, out2, 2, (uint64_t)Nepi, (uint64_t)M, (uint64_t)ldo2, 32)) return VITK_ERR_TMAP;
+            } else {
+                if (make_tmap_2d_store(&tmO, out, esz, (uint64_t)Nepi, (uint64_t)M, (uint64_t)ldo, 32)) return VITK_ERR_TMAP;
+            }
+            g.tma_out = 1;
+        }
+    }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (pair) return dispatch_gemm2(a_mn_major != 0, b_mn_major != 0, epilogue, tmA, tmB, g, st);
-    if (BN == 256) return dispatch_gemm<256>(a_mn_major != 0, b_mn_major != 0, epilogue, tmA, tmB, g, st);
-    return dispatch_gemm<128>(a_mn_major != 0, b_mn_major != 0, epilogue, tmA, tmB, g, st);
+    if (pair) return dispatch_gemm2(a_mn_major != 0, b_mn_major != 0, epilogue, tmA, tmB, tmO, tmO2, g, st);
+    if (BN == 256) return dispatch_gemm<256>(a_mn_major != 0, b_mn_major != 0, epilogue, tmA, tmB, tmO, tmO2, g, st);
+    return dispatch_gemm<128>(a_mn_major != 0, b_mn_major != 0, epilogue, tmA, tmB, tmO, tmO2, g, st);
 }
 
 extern "C" int vitk_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,

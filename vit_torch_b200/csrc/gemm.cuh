@@ -47,6 +47,7 @@ struct GemmArgs {
     int nbatch_h, nbatch_b;
     long long so_h, so_b;    // out strides (elements) per inner / outer batch index
     int a_perm[3], b_perm[3];  // tensor-map dim 1+i takes logical coordinate perm[i] (0 = row, 1 = batch_h, 2 = batch_b)
+    int tma_out;    // 1: `out` (and BIAS_GELU's second output) leave through TMA stores (tensor maps tmO / tmO2)
     int dbg;        // VITK_GEMM_DBG experiment switches (0 in production): 1 no L2 prefetch, 2 plain loads, 4 no loads, 8 no stores
     float* colsum;  // optional fp32 [N]: += column sums of the values stored to `out` (bias gradient of the next Linear)
 };
@@ -57,15 +58,29 @@ constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARP0 = 4;
 constexpr int GEMM_EPI_WARPS = 8;
 
-template <int BN> struct GemmCfg {
+// Outputs leave through TMA stores: each epilogue warp stages [32 rows x 64 B] (16 fp32 / 32 bf16 columns, SWIZZLE_64B)
+// in its own 2 KB shared-memory buffer per output and one elected lane issues cp.async.bulk.tensor. Row-per-lane LSU
+// stores cost one L1 tag cycle per 32-byte sector (32 distinct lines per warp instruction): at 1 sector/clk/SM the
+// 310 MB that the fc1 epilogue writes are 37 us of LSU time, the same order as the MMA time of the tile.
+constexpr int EPI_STG_BYTES = 2048;
+template <int EPI> struct EpiSmem {
+    static constexpr int kOutBufs = (EPI == EPI_ATOMIC_F32 || EPI == EPI_TOKENS_F32) ? 0 : (EPI == EPI_BIAS_GELU ? 2 : 1);
+    static constexpr int STG_BYTES = kOutBufs * GEMM_EPI_WARPS * EPI_STG_BYTES;
+};
+
+template <int BN, int EPI> struct GemmCfg {
     static constexpr int A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
     static constexpr int B_STAGE_BYTES = BN * GEMM_BK * 2;       // 32 KB (BN=256) / 16 KB (BN=128)
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = 256;
     static constexpr int VEC_BYTES = GEMM_EPI_WARPS * 2 * (BN / 2) * 4;  // per epilogue warp: bias | gamma of its columns
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + VEC_BYTES + 1024;  // +1 KB: align
+    static constexpr int STG_BYTES = EpiSmem<EPI>::STG_BYTES;
+    static constexpr int FIXED_BYTES = BAR_BYTES + VEC_BYTES + STG_BYTES + 2048;  // +2 KB: two 1 KB alignments
+    static constexpr int MAX_STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int FIT_STAGES = (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = FIT_STAGES < MAX_STAGES ? FIT_STAGES : MAX_STAGES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
 };
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -219,12 +234,17 @@ template <int BN, int EPI> struct EpilogueWarp {
     const int lane, quarter, half;
     float* wvec;  // per-warp staging of this tile's bias / gamma columns: [bias COLS_PER_WARP | gamma COLS_PER_WARP]
     uint32_t wvec_s;
+    uint32_t stg_s;             // this warp's TMA-store staging buffer(s): [kOutBufs][32 rows x 64 B], SWIZZLE_64B
+    const CUtensorMap* tm_out;  // tensor maps of `out` / BIAS_GELU's `out2` (valid when g.tma_out)
+    const CUtensorMap* tm_out2;
     bool has_bias, has_gamma, has_resid, want_out, vec_ok_static;
 
-    __device__ __forceinline__ EpilogueWarp(const GemmArgs& g_, float* svec, int ew, int warp, int lane_)
-        : g(g_), lane(lane_), quarter(warp & 3), half(ew >> 2) {
+    __device__ __forceinline__ EpilogueWarp(const GemmArgs& g_, float* svec, uint8_t* sstg, const CUtensorMap* tmo,
+                                            const CUtensorMap* tmo2, int ew, int warp, int lane_)
+        : g(g_), lane(lane_), quarter(warp & 3), half(ew >> 2), tm_out(tmo), tm_out2(tmo2) {
         wvec = svec + ew * (2 * COLS_PER_WARP);
         wvec_s = smem_u32(wvec);
+        stg_s = smem_u32(sstg + ew * (EpiSmem<EPI>::kOutBufs * EPI_STG_BYTES));
         has_bias = T::kBias && g.bias != nullptr;
         has_gamma = T::kGamma && g.gamma != nullptr;
         has_resid = T::kResid && g.resid != nullptr;
@@ -263,6 +283,11 @@ template <int BN, int EPI> struct EpilogueWarp {
         }
         R.out = want_out ? static_cast<void*>(reinterpret_cast<char*>(g.out) + (ooff + orow * g.ldo + n0) * OUT_ESZ)
                          : nullptr;
+    }
+
+    // all bulk stores issued by this warp have completed (call once before the kernel ends)
+    __device__ __forceinline__ void finish() const {
+        if (g.tma_out != 0 && EpiSmem<EPI>::kOutBufs > 0 && lane == 0) tma_store_wait<0>();
     }
 
     // L2 prefetch of the accumulator-independent operand rows (residual / GELU') of a future tile
@@ -319,6 +344,8 @@ template <int BN, int EPI> struct EpilogueWarp {
         // operand ring: chunk c's residual / GELU' segment of this lane's row (vector path only)
         uint32_t opq[PF][T::kOpWords];
         auto chunk_is_vec = [&](int c) { return vec_ok_static && n0 + c * 16 + 16 <= g.N; };
+        // TMA stores only when this warp's whole column slab is in range (boxes may span two chunks)
+        const bool use_tma = g.tma_out != 0 && EpiSmem<EPI>::kOutBufs > 0 && n0 + COLS_PER_WARP <= g.N;
         auto fetch_chunk = [&](int c, uint32_t* dst) {
             if (!R.ok || !chunk_is_vec(c)) return;
             if (g.dbg & 4) return;
@@ -413,6 +440,50 @@ template <int BN, int EPI> struct EpilogueWarp {
                         }
                     }
                     }
+                    if (use_tma) {
+                        // ---- TMA store: stage this chunk in the warp's swizzled buffer; one lane issues the copy
+                        if constexpr (EpiSmem<EPI>::kOutBufs > 0) {
+                            constexpr int CHUNKS_PER_BOX = T::kOutF32 ? 1 : 2;   // 64-byte rows: 16 fp32 / 32 bf16 columns
+                            const int sub = c % CHUNKS_PER_BOX;
+                            if (sub == 0) {
+                                // the previous TMA store out of this buffer must have finished reading it
+                                if (lane == 0) tma_store_wait_read<0>();
+                                __syncwarp();
+                            }
+                            const uint32_t rowb = stg_s + lane * 64;
+                            const int sw = (lane >> 1) & 3;
+                            if constexpr (T::kOutF32) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    sts_u4(rowb + ((q ^ sw) << 4), fo[4 * q], fo[4 * q + 1], fo[4 * q + 2], fo[4 * q + 3]);
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 2; ++q) {
+                                    const int unit = sub * 2 + q;
+                                    if (R.out != nullptr)
+                                        sts_u4(rowb + ((unit ^ sw) << 4), ho[4 * q], ho[4 * q + 1], ho[4 * q + 2], ho[4 * q + 3]);
+                                    if constexpr (EPI == EPI_BIAS_GELU)
+                                        sts_u4(rowb + EPI_STG_BYTES + ((unit ^ sw) << 4), ho2[4 * q], ho2[4 * q + 1],
+                                               ho2[4 * q + 2], ho2[4 * q + 3]);
+                                }
+                            }
+                            if (sub == CHUNKS_PER_BOX - 1) {
+                                fence_proxy_async_smem();
+                                __syncwarp();
+                                if (lane == 0 && !(g.dbg & 8)) {
+                                    const int col = n0 + (c - (CHUNKS_PER_BOX - 1)) * 16;
+                                    const int row0 = m_tile * GEMM_BM + quarter * 32;  // rows >= M are clipped by TMA
+                                    if (EPI != EPI_BIAS_GELU || want_out) tma_store_2d_s(tm_out, stg_s, col, row0);
+                                    if constexpr (EPI == EPI_BIAS_GELU)
+                                        tma_store_2d_s(tm_out2, stg_s + EPI_STG_BYTES, col, row0);
+                                    tma_store_commit();
+                                }
+                            }
+                        }
+                        if constexpr (EPI == EPI_RESID_F32) {  // optional bf16 copy of the branch output (LayerScale models)
+                            if (R.ok && R.out2 != nullptr) stg256(R.out2 + c * 16, ho2);
+                        }
+                    } else
                     if (R.ok && !(g.dbg & 8)) {
                         if constexpr (EPI == EPI_ATOMIC_F32) {
                             float* o = reinterpret_cast<float*>(R.out) + c * 16;
@@ -489,8 +560,9 @@ template <int BN, int EPI> struct EpilogueWarp {
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
-    using Cfg = GemmCfg<BN>;
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2, const GemmArgs g) {
+    using Cfg = GemmCfg<BN, EPI>;
     constexpr int STAGES = Cfg::STAGES;
 
     extern __shared__ uint8_t smem_raw[];
@@ -505,6 +577,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]   epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     float* svec = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);  // per-warp bias | gamma
+    uint8_t* sstg = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + Cfg::VEC_BYTES) + 1023) &
+        ~uintptr_t(1023));  // TMA-store staging, 2 KB per epilogue warp and output
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -645,7 +720,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp >= GEMM_EPI_WARP0) {
         // ===================== epilogue =====================
         const int ew = warp - GEMM_EPI_WARP0;
-        EpilogueWarp<BN, EPI> epi(g, svec, ew, warp, lane);
+        EpilogueWarp<BN, EPI> epi(g, svec, sstg, &tmO, &tmO2, ew, warp, lane);
         int as = 0;
         uint32_t aphase = 0;
         auto decode = [&](int un, int& m_tile, int& n_tile, int& batch) {
@@ -669,6 +744,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                      [&]() { if (lane == 0) mbar_arrive(&tempty_bar[as]); });
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
+        epi.finish();
     }
 
     tc_fence_before_sync();

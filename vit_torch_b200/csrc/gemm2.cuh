@@ -17,22 +17,26 @@
 
 namespace vitk {
 
-struct Gemm2Cfg {
+template <int EPI> struct Gemm2Cfg {
     static constexpr int BN = 256;
     static constexpr int A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;        // 16 KB: this CTA's 128 rows of A
     static constexpr int B_STAGE_BYTES = (BN / 2) * GEMM_BK * 2;       // 16 KB: this CTA's half of the B tile
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // 32 KB
-    static constexpr int STAGES = 6;
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = 256;
     static constexpr int VEC_BYTES = GEMM_EPI_WARPS * 2 * (BN / 2) * 4;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + VEC_BYTES + 1024;
+    static constexpr int STG_BYTES = EpiSmem<EPI>::STG_BYTES;           // TMA-store staging
+    static constexpr int FIXED_BYTES = BAR_BYTES + VEC_BYTES + STG_BYTES + 2048;
+    static constexpr int FIT_STAGES = (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = FIT_STAGES < 6 ? FIT_STAGES : 6;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
 };
 
 template <bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
-    using Cfg = Gemm2Cfg;
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2, const GemmArgs g) {
+    using Cfg = Gemm2Cfg<EPI>;
     constexpr int BN = Cfg::BN;
     constexpr int STAGES = Cfg::STAGES;
 
@@ -49,6 +53,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* tempty_bar = bars + 2 * STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     float* svec = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
+    uint8_t* sstg = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + Cfg::VEC_BYTES) + 1023) &
+        ~uintptr_t(1023));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -163,7 +170,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else if (warp >= GEMM_EPI_WARP0) {
         // ===================== epilogue (both CTAs, own 128 rows) =====================
         const int ew = warp - GEMM_EPI_WARP0;
-        EpilogueWarp<BN, EPI> epi(g, svec, ew, warp, lane);
+        EpilogueWarp<BN, EPI> epi(g, svec, sstg, &tmO, &tmO2, ew, warp, lane);
         int as = 0;
         uint32_t aphase = 0;
         int m_unit, n_tile, split;
@@ -182,6 +189,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                      [&]() { if (lane == 0) mbar_arrive_leader(&tempty_bar[as]); });
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
+        epi.finish();
     }
 
     // no CTA may exit (or free TMEM) while its peer can still touch its shared memory, barriers or TMEM

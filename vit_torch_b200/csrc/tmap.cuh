@@ -98,6 +98,16 @@ inline int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, 
     return make_tmap(out, ptr, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
 }
 
+// 2-D map over a row-major [rows, cols] OUTPUT (bf16 or fp32) for TMA stores of [box_rows x 64 bytes] SWIZZLE_64B boxes.
+inline int make_tmap_2d_store(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t cols, uint64_t rows,
+                              uint64_t pitch_elems, uint32_t box_rows) {
+    uint64_t dims[2] = {cols, rows};
+    uint64_t strides[1] = {pitch_elems * (uint64_t)elem_bytes};
+    uint32_t box[2] = {(uint32_t)(64 / elem_bytes), box_rows};
+    return make_tmap(out, ptr, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B,
+                     elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+}
+
 // 4-D bf16 map over a batched row-major operand: logical dims (inner | rows, batch_h, batch_b) with element strides
 // (1 | pitch, stride_h, stride_b). The three outer dims are emitted in order of increasing stride (the driver wants
 // each stride to be a multiple of the previous one); perm[i] tells the kernel which logical coordinate
