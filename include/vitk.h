@@ -161,6 +161,15 @@ int vitk_attn_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_b
                   void* dqkv_bf16, int B, int N, int H, int d, float scale, void* stream);
 
 /*
+ * Single-kernel attention backward (d = 64): S / dP and the elementwise pass are computed once per (key block, query
+ * tile); dV, dK accumulate in TMEM, dQ tiles are summed across key blocks with fp32 atomics into the caller-provided
+ * workspace dq_f32_ws [B*N, H*d] (zeroed inside) and then written as bf16 into dqkv. Launches: delta pre-pass, memset,
+ * fused kernel, conversion. Same inputs / outputs as vitk_attn_bwd; dQ is not bit-reproducible run to run (atomics).
+ */
+int vitk_attn_bwd_fused(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2, float* delta,
+                        float* dq_f32_ws, void* dqkv_bf16, int B, int N, int H, int d, float scale, void* stream);
+
+/*
  * CaiT talking-heads mixing (models/cait.py:116-125), forward: S fp32 [B,H,N,Np] (raw q.k logits, row pitch Np >= N,
  * Np % 8 == 0) -> Pm bf16 [B,H,N,Np] = Ww softmax_j(scale*Wl S + bl) + bw (pad columns zero); rowmax/rowsum fp32
  * [B,H,N] are saved for backward. wl/ww fp32 [H,H] (= proj_l.weight / proj_w.weight), bl/bw fp32 [H]. H in {2,4,6,8,16}.

@@ -38,15 +38,19 @@ def test_attn_fwd(B, N, H, d):
     assert e_l <= 1e-3
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("B,N,H,d", CASES)
-def test_attn_bwd(B, N, H, d):
+def test_attn_bwd(B, N, H, d, fused):
+    """fused=False: the two deterministic kernels (default); fused=True: the single-kernel backward (d = 64 only)."""
     from vit_torch_b200 import ops
+    if fused and d != 64:
+        pytest.skip("single-kernel backward is d = 64 only")
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + N + 7)
     qkv = (torch.randn((B * N, 3 * H * d), device="cuda", generator=g) * 1.2).to(torch.bfloat16)
     dout = torch.randn((B * N, H * d), device="cuda", generator=g).to(torch.bfloat16)
     scale = d ** -0.5
     out, lse2 = ops.attn_fwd(qkv, B, N, H, d, scale)
-    dqkv = ops.attn_bwd(qkv, out, dout, lse2, B, N, H, d, scale)
+    dqkv = ops.attn_bwd(qkv, out, dout, lse2, B, N, H, d, scale, fused=fused)
     x = qkv.float().requires_grad_(True)
     ro, _ = ref_attn(x, B, N, H, d, scale)
     ro.backward(dout.float())

@@ -162,14 +162,27 @@ def attn_fwd(qkv, B, N, H, d, scale):
     return out, lse2
 
 
-def attn_bwd(qkv, out, dout, lse2, B, N, H, d, scale):
-    """Returns dqkv bf16 [B*N, 3*H*d] (dQ | dK | dV in the qkv Linear output layout)."""
+# The single-kernel backward (attn_bwd_fused.cu) is parity-tested but not the default: at B200 it measures 942 us vs
+# 950 us (two kernels) on ViT-B/8 bs64 and 291 us vs 240 us on ViT-B/16 bs128 (profiles/r01_summary_v3.md).
+_ATTN_BWD_FUSED = __import__("os").environ.get("VITK_ATTN_BWD_FUSED", "0") == "1"
+
+
+def attn_bwd(qkv, out, dout, lse2, B, N, H, d, scale, fused=None):
+    """Returns dqkv bf16 [B*N, 3*H*d] (dQ | dK | dV in the qkv Linear output layout). fused=True selects the
+    single-kernel backward (d = 64), fused=None follows VITK_ATTN_BWD_FUSED."""
     global launch_count
     _need_cuda(qkv, out, dout, lse2)
     assert dout.dtype == torch.bfloat16 and dout.is_contiguous() and out.is_contiguous() and qkv.is_contiguous()
     dqkv = torch.empty_like(qkv)
     delta = torch.empty_like(lse2)
     lib = _lib.load()
+    if d == 64 and N <= 8192 and (_ATTN_BWD_FUSED if fused is None else fused):
+        # single-kernel backward; dQ tiles of different key blocks meet in an fp32 workspace (zeroed by the library)
+        dq32 = torch.empty((B * N, H * d), dtype=torch.float32, device=qkv.device)
+        check(lib.vitk_attn_bwd_fused(ptr(qkv), ptr(out), ptr(dout), ptr(lse2), ptr(delta), ptr(dq32), ptr(dqkv), B, N,
+                                      H, d, scale, _stream()), "vitk_attn_bwd_fused")
+        launch_count += 3
+        return dqkv
     check(lib.vitk_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse2), ptr(delta), ptr(dqkv), B, N, H, d, scale,
                             _stream()), "vitk_attn_bwd")
     launch_count += 2
