@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="DP: all-reduce after backward instead of overlapped")
+    ap.add_argument("--no-graph", action="store_true", help="single GPU: launch every kernel eagerly (no CUDA graph)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -222,7 +223,7 @@ def main():
         for p in model.parameters():
             dist.broadcast(p.data, 0)
     trainer = train.Trainer(model, lr=1e-3, momentum=0.9, reducer=GradAllReducer(model, overlap=not args.no_overlap)
-                            if world > 1 else None)
+                            if world > 1 else None, graph=(world == 1 and not args.no_graph))
 
     x_dev, y_dev = synth_batch(bs, size, 1000 + rank, dev)
     x_host = torch.empty((bs, 3, size, size), dtype=torch.float32).pin_memory()
@@ -254,21 +255,29 @@ def main():
         return trainer.step(x_dev, y_dev)
 
     def step_e2e():
-        xb = x_host.to(dev, non_blocking=True)
-        yb = y_host.to(dev, non_blocking=True)
-        loss = trainer.step(xb, yb)
+        st = trainer.static_inputs() if trainer.use_graph else None
+        if st is not None:                                # captured step: H2D straight into its input buffers
+            st[0].copy_(x_host, non_blocking=True)
+            st[1].copy_(y_host, non_blocking=True)
+            loss = trainer.step_static()
+        else:
+            xb = x_host.to(dev, non_blocking=True)
+            yb = y_host.to(dev, non_blocking=True)
+            loss = trainer.step(xb, yb)
         return loss.item()                                # device -> host read of the step result
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()          # nvidia-smi needs ~1 s to come up: start it before the warm-up
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3)):                  # (graph mode: 2 eager steps, then the capture step)
         step_resident()
     l0 = ops.launch_count
     t_begin = time.time()
     ms, loss = timed(step_resident, args.steps)
     t_end = time.time()
     launches = (ops.launch_count - l0) + trainer.extra_launches_per_step * args.steps
+    if trainer.use_graph and trainer.launches_per_step:
+        launches = trainer.launches_per_step * args.steps  # replays do not pass through the Python launch counter
     value = world * bs * args.steps / (ms * 1e-3)
 
     e2e = None
@@ -285,7 +294,7 @@ def main():
     ops.gemm_timing_begin()
     barrier()
     for _ in range(args.steps):
-        step_resident()
+        trainer._step_eager(x_dev, y_dev)                 # per-launch events need eager launches
     barrier()
     gemm_ms, gemm_launches = ops.gemm_timing_end()
     gemm_fl = gemm_flops_per_image(N, D, L, P) * bs * args.steps
@@ -314,7 +323,8 @@ def main():
             "config": {"workload": f"{name} fine-tune (fwd+CE+bwd+SGD momentum 0.9) 224x224 synthetic, random init",
                        "batch_per_gpu": bs, "global_batch": bs * world, "tokens": N, "parallelism": f"dp{world}",
                        "l2": "working set per step (>8 GB of activations) far exceeds the 126 MB L2; no explicit flush",
-                       "numerics": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream + master weights"},
+                       "numerics": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream + master weights",
+                       "launch": "whole step captured in one CUDA graph" if trainer.use_graph else "eager launches"},
             "step_tflops_per_gpu": step_fl / (ms / args.steps * 1e-3) / 1e12,
             "step_frac_of_bf16_peak": step_fl / (ms / args.steps * 1e-3) / 1e12 / pk["bf16_sustained"],
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

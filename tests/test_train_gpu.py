@@ -64,3 +64,23 @@ def test_lineareval_flow():
         losses.append(loss.item())
     assert all(p.grad is None for p in backbone.parameters())
     assert losses[-1] < losses[0]
+
+
+def test_graph_step_matches_eager_step():
+    """Trainer(graph=True) replays the captured step: same losses as eager launches on the same data."""
+    import torch
+    from vit_torch_b200 import models, train
+    torch.manual_seed(0)
+    xs = [torch.randn(4, 3, 224, 224, device="cuda") for _ in range(6)]
+    ys = [torch.randint(0, 10, (4,), device="cuda") for _ in range(6)]
+    losses = {}
+    for mode in (False, True):
+        torch.manual_seed(1)
+        m = models.dino_vits16(pretrained=False).cuda()
+        train.reset_parameters_like_zoo(m)
+        tr = train.Trainer(m, lr=1e-2, graph=mode)
+        losses[mode] = [tr.step(x, y).item() for x, y in zip(xs, ys)]
+        if mode:
+            assert tr.static_inputs() is not None and tr.launches_per_step > 100
+    for a, b in zip(losses[False], losses[True]):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(a)), (losses[False], losses[True])

@@ -97,14 +97,24 @@ class FusedSGD(torch.optim.Optimizer):
 
 
 class Trainer:
-    def __init__(self, model: nn.Module, lr: float = 1e-3, momentum: float = 0.9, reducer=None, fused_opt: bool = True):
+    """The reference's optimisation step (utils_network.py:406-452). With graph=True the whole step -- forward, loss,
+    backward, fused optimiser: ~300 kernel launches -- is captured once into a CUDA graph on static input buffers and
+    replayed (single-GPU only; the arithmetic and the launch sequence are exactly those of the eager step)."""
+
+    def __init__(self, model: nn.Module, lr: float = 1e-3, momentum: float = 0.9, reducer=None, fused_opt: bool = True,
+                 graph: bool = False):
         self.model = model
         self.reducer = reducer
         params = [p for p in model.parameters() if p.requires_grad]
         self.opt = (FusedSGD if fused_opt else torch.optim.SGD)(params, lr=lr, momentum=momentum)
         self.extra_launches_per_step = 0
+        self.use_graph = bool(graph) and reducer is None
+        self._graph = None
+        self._sx = self._sy = self._sloss = None
+        self._eager_steps = 0
+        self.launches_per_step = None   # libvitk launches inside one captured step
 
-    def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    def _step_eager(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         out = self.model(x)
         loss = F.cross_entropy(out, y)
         self.opt.zero_grad(set_to_none=True)
@@ -113,3 +123,39 @@ class Trainer:
             self.reducer.finish()
         self.opt.step()
         return loss.detach()
+
+    def _capture(self, x: torch.Tensor, y: torch.Tensor) -> None:
+        from . import ops
+        # (no warm-up step here: it would be an extra optimisation step; step() has already run two eager ones)
+        self._sx, self._sy = x.clone(), y.clone()
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count
+        with torch.cuda.graph(self._graph):
+            self._sloss = self._step_eager(self._sx, self._sy)
+        self.launches_per_step = ops.launch_count - n0
+
+    def static_inputs(self):
+        """(images, labels) device buffers the captured step reads; fill them (e.g. `copy_` from pinned host memory)
+        and call step_static(). None before the graph exists."""
+        return (self._sx, self._sy) if self._graph is not None else None
+
+    def step_static(self) -> torch.Tensor:
+        self._graph.replay()
+        return self._sloss
+
+    def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if not self.use_graph:
+            return self._step_eager(x, y)
+        if self._graph is None:
+            if self._eager_steps < 2:        # first steps eager: bf16 weight cache, optimiser state, autotuned plans
+                self._eager_steps += 1
+                return self._step_eager(x, y)
+            self._capture(x, y)
+        if x.shape != self._sx.shape or y.shape != self._sy.shape or x.dtype != self._sx.dtype:
+            return self._step_eager(x, y)    # a different batch shape (e.g. the last batch of an epoch)
+        if x.data_ptr() != self._sx.data_ptr():
+            self._sx.copy_(x, non_blocking=True)
+        if y.data_ptr() != self._sy.data_ptr():
+            self._sy.copy_(y, non_blocking=True)
+        return self.step_static()
