@@ -254,16 +254,38 @@ def main():
     def step_resident():
         return trainer.step(x_dev, y_dev)
 
+    # e2e input pipeline: every step's batch goes pinned host -> device inside the timed region, on a copy stream so
+    # that the transfer of batch i+1 overlaps step i (what DataLoader(pin_memory=True) + non_blocking copies give the
+    # reference loop, utils_network.py:409-410); the step waits on the copy's event, the loss is read back every step.
+    copy_stream = torch.cuda.Stream()
+    stage_x = [torch.empty_like(x_dev) for _ in range(2)]
+    stage_y = [torch.empty_like(y_dev) for _ in range(2)]
+    stage_ev = [torch.cuda.Event() for _ in range(2)]
+    e2e_state = {"it": 0, "primed": False}
+
+    def prefetch(k):
+        copy_stream.wait_stream(torch.cuda.current_stream())   # the buffer's previous consumer has been enqueued
+        with torch.cuda.stream(copy_stream):
+            stage_x[k].copy_(x_host, non_blocking=True)
+            stage_y[k].copy_(y_host, non_blocking=True)
+            stage_ev[k].record(copy_stream)
+
     def step_e2e():
+        k = e2e_state["it"] & 1
+        if not e2e_state["primed"]:
+            prefetch(k)
+            e2e_state["primed"] = True
+        torch.cuda.current_stream().wait_event(stage_ev[k])
         st = trainer.static_inputs() if trainer.use_graph else None
-        if st is not None:                                # captured step: H2D straight into its input buffers
-            st[0].copy_(x_host, non_blocking=True)
-            st[1].copy_(y_host, non_blocking=True)
+        if st is not None:                                # captured step reads fixed buffers: device-to-device hand-over
+            st[0].copy_(stage_x[k], non_blocking=True)
+            st[1].copy_(stage_y[k], non_blocking=True)
+            prefetch(k ^ 1)                               # next batch's H2D overlaps this step
             loss = trainer.step_static()
         else:
-            xb = x_host.to(dev, non_blocking=True)
-            yb = y_host.to(dev, non_blocking=True)
-            loss = trainer.step(xb, yb)
+            prefetch(k ^ 1)
+            loss = trainer.step(stage_x[k], stage_y[k])
+        e2e_state["it"] += 1
         return loss.item()                                # device -> host read of the step result
 
     sampler = ClockSampler(local)
@@ -284,6 +306,8 @@ def main():
     if not args.no_e2e:
         for _ in range(2):
             step_e2e()
+        torch.cuda.synchronize()
+        e2e_state["primed"] = False                       # the first timed step issues its own H2D copy
         ms_e, _ = timed(step_e2e, args.steps)
         e2e = {"value": world * bs * args.steps / (ms_e * 1e-3), "unit": "images/s",
                "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4,
