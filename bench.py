@@ -156,7 +156,7 @@ def run_reference(args):
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "loss": float(loss),
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def cpu_baseline(args):
@@ -179,7 +179,25 @@ def cpu_baseline(args):
                       f"({dt:.1f} s) on the GPU box host"}
 
 
+def _emit(line: dict) -> None:
+    """Write THE one JSON line to the process's original stdout (see _claim_stdout)."""
+    os.write(_STDOUT_FD, (json.dumps(line) + "\n").encode())
+
+
+_STDOUT_FD = 1
+
+
+def _claim_stdout() -> None:
+    """Keep stdout clean for the single JSON line: libraries (NCCL prints its version banner on stdout) and stray
+    prints are redirected to stderr; _emit() writes to the saved descriptor."""
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -354,7 +372,7 @@ def main():
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "loss": float(loss),
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
