@@ -209,6 +209,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="DP: all-reduce after backward instead of overlapped")
+    ap.add_argument("--nccl-ctas", type=int, default=4,
+                    help="DP: thread blocks left to the overlapped NCCL all-reduce (0 = NCCL default, GEMMs use every SM)")
     ap.add_argument("--no-graph", action="store_true", help="single GPU: launch every kernel eagerly (no CUDA graph)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -230,6 +232,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        from vit_torch_b200.dist import configure_sm_partition
+        configure_sm_partition(args.nccl_ctas)
         dist.init_process_group("nccl", device_id=dev)
 
     name, bs_default, size, N, D, L, H, P = WORKLOADS[args.workload]

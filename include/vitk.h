@@ -37,6 +37,10 @@ extern "C" {
 /* Library/ABI version and build info. */
 int vitk_abi_version(void);
 
+/* Size the persistent kernels' grids for at most n SMs (0 = all). Data-parallel runs leave a few SMs to the NCCL
+ * kernels that overlap backward (vit_torch_b200/dist.py). Process-wide. */
+int vitk_set_sm_limit(int n);
+
 /*
  * D[M,N] = A[M,K] * B[N,K]^T on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM), fused epilogue.
  *   a_mn_major = 0: A stored [M, lda] (K contiguous);  1: A stored [K, lda] (M contiguous)

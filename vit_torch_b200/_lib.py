@@ -22,6 +22,7 @@ ERRORS = {
 _P, _I, _L, _F = c_void_p, c_int, c_longlong, c_float
 SIGNATURES = {
     "vitk_abi_version": [],
+    "vitk_set_sm_limit": [_I],
     "vitk_gemm_bf16": [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _L, _P, _L, _P, _L, _P, _L, _I, _P],
     "vitk_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
     "vitk_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P],

@@ -45,11 +45,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 }
 
 // ---- CTA-pair kernel (gemm2.cuh) ----
-static int max_clusters() {
-    static int cached = 0;
-    if (cached == 0) cached = sm_count() / 2 > 0 ? sm_count() / 2 : 1;
-    return cached;
-}
+static int max_clusters() { return sm_count() / 2 > 0 ? sm_count() / 2 : 1; }
 
 // VITK_GEMM_2CTA=0 keeps every GEMM on the 1-CTA kernel (A/B measurements)
 static bool use_2cta() {
@@ -261,6 +257,12 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
     if (pair) return dispatch_gemm2(a_mn_major != 0, b_mn_major != 0, epilogue, tmA, tmB, tmO, tmO2, g, st);
     if (BN == 256) return dispatch_gemm<256>(a_mn_major != 0, b_mn_major != 0, epilogue, tmA, tmB, tmO, tmO2, g, st);
     return dispatch_gemm<128>(a_mn_major != 0, b_mn_major != 0, epilogue, tmA, tmB, tmO, tmO2, g, st);
+}
+
+extern "C" int vitk_set_sm_limit(int n) {
+    if (n < 0) return VITK_ERR_ARG;
+    sm_limit_ref() = n;
+    return VITK_OK;
 }
 
 extern "C" int vitk_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,

@@ -135,6 +135,12 @@ inline int make_tmap_4d_bf16(CUtensorMap* out, int perm[3], const void* ptr, uin
     return make_tmap(out, ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
 }
 
+// SMs the persistent kernels size their grids for. vitk_set_sm_limit() lowers it (data-parallel runs leave a few SMs
+// to the NCCL kernels: a statically scheduled persistent CTA that has to wait for an SM doubles its kernel's time).
+inline int& sm_limit_ref() {
+    static int limit = 0;  // 0 = no limit
+    return limit;
+}
 inline int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -143,7 +149,8 @@ inline int sm_count() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
     }
-    return n;
+    const int lim = sm_limit_ref();
+    return (lim > 0 && lim < n) ? lim : n;
 }
 
 }  // namespace vitk

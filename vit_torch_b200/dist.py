@@ -16,6 +16,23 @@ import torch.distributed as dist
 from . import functional as Fn
 
 
+def configure_sm_partition(nccl_ctas: int = 4) -> None:
+    """Call BEFORE dist.init_process_group. Caps the NCCL kernels at `nccl_ctas` thread blocks (NCCL_MAX_CTAS, unless
+    the user already set it) and sizes the persistent GEMM grids for the remaining SMs. The GEMMs are statically
+    scheduled, one CTA per SM: if an overlapping all-reduce kernel holds an SM when a GEMM launches, that GEMM's late CTA
+    still owns 1/148 of the tiles and the kernel takes twice as long; leaving the SMs free costs nccl_ctas/148 of GEMM
+    throughput instead. Measured on 2 B200 (ViT-B/16 bs128): NCCL default 21.09 ms/step, 16 blocks 20.87, 8 blocks 20.60,
+    4 blocks 20.16; 4 blocks still move the 343 MB of fp32 gradients well inside one backward pass."""
+    import os
+
+    from . import ops
+    if nccl_ctas <= 0:
+        return
+    os.environ.setdefault("NCCL_MAX_CTAS", str(nccl_ctas))
+    n = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    ops.set_sm_limit(max(n - int(os.environ["NCCL_MAX_CTAS"]), n // 2))
+
+
 class GradAllReducer:
     def __init__(self, model: torch.nn.Module, process_group=None, overlap: bool = True):
         self.model = model

@@ -404,3 +404,8 @@ def sgd_momentum_multi(table, chunk_map, num_chunks, lr, momentum, grad_scale=1.
 
 
 sgd_momentum_multi = _timed(sgd_momentum_multi) if "_timed" in globals() else sgd_momentum_multi
+
+
+def set_sm_limit(n: int) -> None:
+    """Size persistent-kernel grids for at most n SMs (0 = all). See vitk_set_sm_limit."""
+    check(_lib.load().vitk_set_sm_limit(int(n)), "vitk_set_sm_limit")

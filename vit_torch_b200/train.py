@@ -99,7 +99,8 @@ class FusedSGD(torch.optim.Optimizer):
 class Trainer:
     """The reference's optimisation step (utils_network.py:406-452). With graph=True the whole step -- forward, loss,
     backward, fused optimiser: ~300 kernel launches -- is captured once into a CUDA graph on static input buffers and
-    replayed (single-GPU only; the arithmetic and the launch sequence are exactly those of the eager step)."""
+    replayed (single GPU only: capturing the overlapped NCCL all-reduces measured no gain on 2 GPUs -- 20.11 vs 20.16
+    ms/step -- and hung at process-group teardown; the arithmetic and launch sequence are those of the eager step)."""
 
     def __init__(self, model: nn.Module, lr: float = 1e-3, momentum: float = 0.9, reducer=None, fused_opt: bool = True,
                  graph: bool = False):
