@@ -164,6 +164,11 @@ int vitk_attn_fwd(const void* qkv_bf16, void* out_bf16, float* lse2, int B, int 
 int vitk_attn_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2, float* delta,
                   void* dqkv_bf16, int B, int N, int H, int d, float scale, void* stream);
 
+/* vitk_attn_bwd that also accumulates (+=) the column sums of dqkv into dqkv_bias_grad fp32 [3*H*d] -- the gradient of
+ * the qkv Linear bias (db = sum_rows dY) -- from the registers that hold the dQ / dK / dV tiles. */
+int vitk_attn_bwd_ex(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2, float* delta,
+                     void* dqkv_bf16, float* dqkv_bias_grad, int B, int N, int H, int d, float scale, void* stream);
+
 /*
  * Single-kernel attention backward (d = 64): S / dP and the elementwise pass are computed once per (key block, query
  * tile); dV, dK accumulate in TMEM, dQ tiles are summed across key blocks with fp32 atomics into the caller-provided

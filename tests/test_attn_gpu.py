@@ -50,7 +50,9 @@ def test_attn_bwd(B, N, H, d, fused):
     dout = torch.randn((B * N, H * d), device="cuda", generator=g).to(torch.bfloat16)
     scale = d ** -0.5
     out, lse2 = ops.attn_fwd(qkv, B, N, H, d, scale)
-    dqkv = ops.attn_bwd(qkv, out, dout, lse2, B, N, H, d, scale, fused=fused)
+    dbias = torch.ones((3 * H * d,), device="cuda")            # += column sums of dqkv (qkv Linear bias gradient)
+    dqkv = ops.attn_bwd(qkv, out, dout, lse2, B, N, H, d, scale, fused=fused, dbias=dbias)
+    assert nerr(dbias - 1, dqkv.float().sum(0)) <= 5e-3        # fp32 tile sums vs sums of the bf16-rounded outputs
     x = qkv.float().requires_grad_(True)
     ro, _ = ref_attn(x, B, N, H, d, scale)
     ro.backward(dout.float())

@@ -31,7 +31,17 @@ struct AttnBwdArgs {
     const float* lse2;          // [B,H,N]
     float* delta;               // [B,H,N]
     __nv_bfloat16* dqkv;        // [B*N, 3D]
+    float* dbias;               // optional fp32 [3D], += column sums of dqkv (gradient of the qkv Linear bias)
 };
+
+// += column sums of one [rows of this warp x 16 columns] chunk of a gradient tile (invalid rows contribute zero)
+__device__ __forceinline__ void ab_colsum_chunk(float* dst16, const uint32_t* r, bool row_ok, int lane) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = row_ok ? __uint_as_float(r[i]) : 0.f;
+    const float tot = warp_colsum16(v, lane);
+    if ((lane & 1) == 0) atomicAdd(dst16 + warp_colsum16_col(lane), tot);
+}
 
 // write 32 consecutive bf16 columns (chunk c of a 64-column K-major swizzled tile row)
 __device__ __forceinline__ void store_row_chunk_sw128(uint8_t* tile_row, int sw, int c, const float* v) {
@@ -224,6 +234,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
             uint32_t r[16];
             tmem_ld_32x32b_x16(tmem_dq + lane_off + c * 16, r);
             tmem_ld_wait();
+            if (a.dbias != nullptr) ab_colsum_chunk(a.dbias + h * HD + c * 16, r, row_ok, lane);
             if (row_ok) {
                 const float* f = reinterpret_cast<const float*>(r);
                 st_v4(dst + c * 16, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
@@ -426,6 +437,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
             tmem_ld_32x32b_x16(tmem_dk + lane_off + c * 16, rk);
             tmem_ld_32x32b_x16(tmem_dv + lane_off + c * 16, rv);
             tmem_ld_wait();
+            if (a.dbias != nullptr) {
+                ab_colsum_chunk(a.dbias + a.D + h * HD + c * 16, rk, row_ok, lane);
+                ab_colsum_chunk(a.dbias + 2 * a.D + h * HD + c * 16, rv, row_ok, lane);
+            }
             if (row_ok) {
                 const float* f = reinterpret_cast<const float*>(rk);
                 st_v4(dkp + c * 16, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
@@ -471,8 +486,9 @@ static int launch_attn_bwd(const CUtensorMap& q128, const CUtensorMap& q64, cons
 
 using namespace vitk;
 
-extern "C" int vitk_attn_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2,
-                             float* delta, void* dqkv_bf16, int B, int N, int H, int d, float scale, void* stream) {
+static int attn_bwd_impl(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2,
+                         float* delta, void* dqkv_bf16, float* dbias, int B, int N, int H, int d, float scale,
+                         void* stream) {
     if (B <= 0 || N <= 0 || H <= 0 || !(d == 64 || d == 48)) return VITK_ERR_ARG;
     if (!qkv_bf16 || !out_bf16 || !dout_bf16 || !lse2 || !delta || !dqkv_bf16) return VITK_ERR_ARG;
     CUtensorMap q128, q64, do128, do64;
@@ -490,7 +506,20 @@ extern "C" int vitk_attn_bwd(const void* qkv_bf16, const void* out_bf16, const v
     a.lse2 = lse2;
     a.delta = delta;
     a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv_bf16);
+    a.dbias = dbias;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (d == 64) return launch_attn_bwd<64>(q128, q64, do128, do64, a, st);
     return launch_attn_bwd<48>(q128, q64, do128, do64, a, st);
+}
+
+extern "C" int vitk_attn_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2,
+                             float* delta, void* dqkv_bf16, int B, int N, int H, int d, float scale, void* stream) {
+    return attn_bwd_impl(qkv_bf16, out_bf16, dout_bf16, lse2, delta, dqkv_bf16, nullptr, B, N, H, d, scale, stream);
+}
+
+extern "C" int vitk_attn_bwd_ex(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2,
+                                float* delta, void* dqkv_bf16, float* dqkv_bias_grad, int B, int N, int H, int d,
+                                float scale, void* stream) {
+    return attn_bwd_impl(qkv_bf16, out_bf16, dout_bf16, lse2, delta, dqkv_bf16, dqkv_bias_grad, B, N, H, d, scale,
+                         stream);
 }

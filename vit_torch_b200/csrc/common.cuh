@@ -456,4 +456,53 @@ __device__ __forceinline__ void red_add_v4_f32(float* p, float a, float b, float
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// ----------------------------------------------------------------------------------------------
+// Column sums over the 32 rows of a warp for the 16 columns of a chunk (lane = row): recursive halving, 16 shuffles.
+// On return lane l (l even) holds the total of column ((l >> 1) & 15) ... see `col_of_lane`.
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+    float a[8];
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float send = up ? v[i] : v[i + 8];
+            const float keep = up ? v[i + 8] : v[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    float b4[4];
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = up ? a[i] : a[i + 4];
+            const float keep = up ? a[i + 4] : a[i];
+            b4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    float c2[2];
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = up ? b4[i] : b4[i + 2];
+            const float keep = up ? b4[i + 2] : b4[i];
+            c2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    float d;
+    {
+        const bool up = lane & 2;
+        const float send = up ? c2[0] : c2[1];
+        const float keep = up ? c2[1] : c2[0];
+        d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;  // column index held by this lane: 8*bit4 + 4*bit3 + 2*bit2 + bit1 of `lane`
+}
+__device__ __forceinline__ int warp_colsum16_col(int lane) {
+    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+
 }  // namespace vitk

@@ -180,8 +180,10 @@ class BlockFn(torch.autograd.Function):
             ops.gemm(dx1b, o, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dprojw)
         if dprojb is not None and not plain1:
             ops.colsum_accum(dx1b, dprojb)
+        attn_dbias_done = False
         if thl_w is None:
-            dqkv = ops.attn_bwd(qkv, o, do, lse2, B, N, H, d, scale)
+            dqkv = ops.attn_bwd(qkv, o, do, lse2, B, N, H, d, scale, dbias=dqkvb)  # qkv bias gradient fused in
+            attn_dbias_done = dqkvb is not None
         else:
             Np = S.shape[-1]
             zeros = lambda t: torch.zeros_like(t, dtype=torch.float32)
@@ -211,7 +213,7 @@ class BlockFn(torch.autograd.Function):
         ops.gemm(dqkv, wqkv, b_mn=True, epilogue=ops.EPI_STORE_BF16, out=dh1)
         if dqkvw is not None:
             ops.gemm(dqkv, h1, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dqkvw)
-        if dqkvb is not None:
+        if dqkvb is not None and not attn_dbias_done:
             ops.colsum_accum(dqkv, dqkvb)
         # ---- LN1 backward + residual; the bf16 copy is handed to the previous block through a side channel
         side_sum = torch.zeros((D,), dtype=torch.float32, device=dev)

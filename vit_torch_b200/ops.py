@@ -167,9 +167,10 @@ def attn_fwd(qkv, B, N, H, d, scale):
 _ATTN_BWD_FUSED = __import__("os").environ.get("VITK_ATTN_BWD_FUSED", "0") == "1"
 
 
-def attn_bwd(qkv, out, dout, lse2, B, N, H, d, scale, fused=None):
+def attn_bwd(qkv, out, dout, lse2, B, N, H, d, scale, fused=None, dbias=None):
     """Returns dqkv bf16 [B*N, 3*H*d] (dQ | dK | dV in the qkv Linear output layout). fused=True selects the
-    single-kernel backward (d = 64), fused=None follows VITK_ATTN_BWD_FUSED."""
+    single-kernel backward (d = 64), fused=None follows VITK_ATTN_BWD_FUSED. dbias (fp32 [3*H*d], optional): += column
+    sums of dqkv = gradient of the qkv Linear bias, produced by the two-kernel backward itself."""
     global launch_count
     _need_cuda(qkv, out, dout, lse2)
     assert dout.dtype == torch.bfloat16 and dout.is_contiguous() and out.is_contiguous() and qkv.is_contiguous()
@@ -182,9 +183,11 @@ def attn_bwd(qkv, out, dout, lse2, B, N, H, d, scale, fused=None):
         check(lib.vitk_attn_bwd_fused(ptr(qkv), ptr(out), ptr(dout), ptr(lse2), ptr(delta), ptr(dq32), ptr(dqkv), B, N,
                                       H, d, scale, _stream()), "vitk_attn_bwd_fused")
         launch_count += 3
+        if dbias is not None:
+            colsum_accum(dqkv, dbias)
         return dqkv
-    check(lib.vitk_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse2), ptr(delta), ptr(dqkv), B, N, H, d, scale,
-                            _stream()), "vitk_attn_bwd")
+    check(lib.vitk_attn_bwd_ex(ptr(qkv), ptr(out), ptr(dout), ptr(lse2), ptr(delta), ptr(dqkv), ptr(dbias), B, N, H, d,
+                               scale, _stream()), "vitk_attn_bwd_ex")
     launch_count += 2
     return dqkv
 
