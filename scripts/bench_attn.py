@@ -17,6 +17,7 @@ def timeit(fn, iters=10, warm=3):
     return s.elapsed_time(e) / iters * 1e-3
 
 rows = []
+tag = "wg2" if os.environ.get("VITK_ATTN_WG2", "1") != "0" else "wg1"
 for (B, N, H, d) in [(2, 197, 6, 64), (128, 197, 12, 64), (64, 785, 12, 64), (128, 196, 8, 48)]:
     qkv = torch.randn(B * N, 3 * H * d, device=dev).bfloat16()
     do = torch.randn(B * N, H * d, device=dev).bfloat16()
@@ -37,4 +38,4 @@ for (B, N, H, d) in [(2, 197, 6, 64), (128, 197, 12, 64), (64, 785, 12, 64), (12
         rows.append(dict(op="attn_bwd", B=B, N=N, H=H, d=d, us=round(t * 1e6, 1), tflops=round(2.5 * fl / t / 1e12, 1)))
         print(rows[-1], flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(rows, open("gpurun_out/bench_attn.json", "w"), indent=1)
+json.dump(rows, open(f"gpurun_out/bench_attn_{tag}.json", "w"), indent=1)

@@ -24,9 +24,13 @@ CASES = [(2, 197, 6, 64), (1, 128, 1, 64), (3, 37, 2, 64), (2, 785, 3, 64), (2, 
          (1, 1297, 2, 64), (2, 198, 3, 64), (4, 256, 2, 64), (2, 1, 2, 64)]
 
 
+@pytest.mark.parametrize("groups", [2, 1])
 @pytest.mark.parametrize("B,N,H,d", CASES)
-def test_attn_fwd(B, N, H, d):
+def test_attn_fwd(B, N, H, d, groups, monkeypatch):
+    """groups=2: eight softmax warps per CTA, two independent online softmaxes merged per row (default);
+    groups=1: the four-warp kernel (VITK_ATTN_WG2=0)."""
     from vit_torch_b200 import ops
+    monkeypatch.setenv("VITK_ATTN_WG2", "1" if groups == 2 else "0")
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + N)
     qkv = (torch.randn((B * N, 3 * H * d), device="cuda", generator=g) * 1.5).to(torch.bfloat16)
     scale = d ** -0.5
@@ -38,13 +42,16 @@ def test_attn_fwd(B, N, H, d):
     assert e_l <= 1e-3
 
 
-@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("variant", ["two_kernel_wg2", "two_kernel_wg1", "fused"])
 @pytest.mark.parametrize("B,N,H,d", CASES)
-def test_attn_bwd(B, N, H, d, fused):
-    """fused=False: the two deterministic kernels (default); fused=True: the single-kernel backward (d = 64 only)."""
+def test_attn_bwd(B, N, H, d, variant, monkeypatch):
+    """two_kernel_wg2: the two deterministic kernels with eight elementwise warps per CTA (default); two_kernel_wg1:
+    the four-warp kernels (VITK_ATTN_WG2=0); fused: the single-kernel backward (d = 64 only)."""
     from vit_torch_b200 import ops
+    fused = variant == "fused"
     if fused and d != 64:
         pytest.skip("single-kernel backward is d = 64 only")
+    monkeypatch.setenv("VITK_ATTN_WG2", "0" if variant == "two_kernel_wg1" else "1")
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + N + 7)
     qkv = (torch.randn((B * N, 3 * H * d), device="cuda", generator=g) * 1.2).to(torch.bfloat16)
     dout = torch.randn((B * N, H * d), device="cuda", generator=g).to(torch.bfloat16)

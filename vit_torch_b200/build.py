@@ -15,8 +15,11 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
-LIB = os.path.join(HERE, "libvitk.so")
-OBJ_DIR = os.path.join(HERE, "build")
+# VITK_NVCC_EXTRA="-DVITK_TRACE" builds an instrumented copy (libvitk_dbg.so, objects in build_dbg/) next to the
+# product library; load it with VITK_LIB=.../libvitk_dbg.so (scripts/trace_attn.py).
+EXTRA = os.environ.get("VITK_NVCC_EXTRA", "").split()
+LIB = os.path.join(HERE, "libvitk_dbg.so" if EXTRA else "libvitk.so")
+OBJ_DIR = os.path.join(HERE, "build_dbg" if EXTRA else "build")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -25,7 +28,7 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
     "-I", os.path.join(ROOT, "include"),
-]
+] + EXTRA
 
 
 def _nvcc() -> str:

@@ -20,6 +20,7 @@
 //     enough, lse2 = m_ref + log2(l) stays exact);
 //   * P_j (bf16, 128B-swizzled K-major smem tile, double-buffered) x V_j (MN-major B operand read from the token-major
 //     tile) accumulates straight into the 64 O columns of TMEM; O is read once at the end.
+#include <cstdlib>
 #include "common.cuh"
 #include "tmap.cuh"
 #include "../../include/vitk.h"
@@ -45,7 +46,12 @@ struct AttnFwdArgs {
     float scale_log2;  // scale * log2(e)
     __nv_bfloat16* out;  // [B*N, D]
     float* lse2;         // [B, H, N]
+    long long* trace;    // instrumented build only (VITK_TRACE), else nullptr
 };
+
+#ifdef VITK_TRACE
+long long* g_attn_trace = nullptr;
+#endif
 
 template <int HD>
 __global__ void __launch_bounds__(AF_THREADS, 2)
@@ -274,6 +280,308 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Two-group variant (default): the same tile pipeline with EIGHT softmax warps per CTA. Group g = warp / 4 owns the key
+// columns [32g, 32g + 32) of every 64-key tile and runs its own online softmax over them (its own reference maximum,
+// running sum and output accumulator O_g in TMEM: PV k-steps 2g, 2g+1 of a tile accumulate into O_g), so the two groups
+// never exchange anything inside the loop; the epilogue merges (m_0, l_0, O_0) and (m_1, l_1, O_1) per row. A thread
+// handles 32 scores per tile instead of 64: the dependent LDTM -> max -> exp -> pack -> STS chain that bounds the
+// per-tile latency is half as long and twice as many warps are there to cover it. Warps whose 32 query rows all lie
+// past the end of the image only take part in the barriers.
+constexpr int AF2_THREADS = 320;                          // warps 0-7 softmax, warp 8 TMA, warp 9 MMA
+constexpr int AF2_NS = 4;                                 // K/V ring stages: a 197-token image is fully in flight at once
+constexpr int AF2_SMEM_Q = 0;                             // (reused for the groups' (m_ref, l) exchange in the epilogue)
+constexpr int AF2_SMEM_K = AF2_SMEM_Q + AF_QTILE;
+constexpr int AF2_SMEM_V = AF2_SMEM_K + AF2_NS * AF_KVTILE;
+constexpr int AF2_SMEM_P = AF2_SMEM_V + AF2_NS * AF_KVTILE;   // 2 buffers [128 x 64] bf16
+constexpr int AF2_SMEM_BAR = AF2_SMEM_P + 2 * AF_QTILE;
+constexpr int AF2_SMEM_BYTES = AF2_SMEM_BAR + 256;
+constexpr uint32_t AF2_TMEM_COLS = 256;                   // S: [0,64)  O_0: [64,128)  O_1: [128,192)
+
+template <int HD>
+__global__ void __launch_bounds__(AF2_THREADS, 2)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                 const __grid_constant__ CUtensorMap tmO, const AttnFwdArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int NS = AF2_NS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AF2_SMEM_BAR);
+    uint64_t* q_full = bars + 0;
+    uint64_t* s_full = bars + 1;
+    uint64_t* s_free = bars + 2;
+    uint64_t* p_full = bars + 3;    // [group][buffer]
+    uint64_t* o_full = bars + 7;    // [2]  PV_j complete (j even / odd), both groups
+    uint64_t* k_full = bars + 9;    // [NS]
+    uint64_t* v_full = k_full + NS;
+    uint64_t* kv_empty = v_full + NS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + NS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qblk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = qblk * AF_BQ;
+    const int nkv = (a.N + AF_BKV - 1) / AF_BKV;
+
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need 1 KB alignment
+    if (warp == 8 && lane == 0) {
+        VITK_TRACE_EV(a.trace, 0);
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmKV);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&p_full[i], 128);
+            mbar_init(&p_full[2 + i], 128);
+            mbar_init(&o_full[i], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 256);
+        fence_mbar_init();
+        mbar_expect_tx(q_full, AF_QTILE);
+        tma_load_2d(smem + AF2_SMEM_Q, &tmQ, q_full, h * HD, b * a.N + q0);
+        for (int j = 0; j < NS && j < nkv; ++j) {
+            mbar_expect_tx(&k_full[j], AF_KVTILE);
+            tma_load_2d(smem + AF2_SMEM_K + j * AF_KVTILE, &tmKV, &k_full[j], (a.H + h) * HD, b * a.N + j * AF_BKV);
+            mbar_expect_tx(&v_full[j], AF_KVTILE);
+            tma_load_2d(smem + AF2_SMEM_V + j * AF_KVTILE, &tmKV, &v_full[j], (2 * a.H + h) * HD, b * a.N + j * AF_BKV);
+        }
+    }
+    if (warp == 9) tmem_alloc<AF2_TMEM_COLS>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 64;   // O_g at tmem_o + 64 g
+
+    if (warp == 8) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int j = NS; j < nkv; ++j) {   // the first NS tiles were issued in the prologue
+                const int s = j % NS;
+                mbar_wait(&kv_empty[s], ((j / NS) & 1) ^ 1);
+                mbar_expect_tx(&k_full[s], AF_KVTILE);
+                tma_load_2d(smem + AF2_SMEM_K + s * AF_KVTILE, &tmKV, &k_full[s], (a.H + h) * HD, b * a.N + j * AF_BKV);
+                mbar_expect_tx(&v_full[s], AF_KVTILE);
+                tma_load_2d(smem + AF2_SMEM_V + s * AF_KVTILE, &tmKV, &v_full[s], (2 * a.H + h) * HD,
+                            b * a.N + j * AF_BKV);
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t q_addr = smem_u32(smem + AF2_SMEM_Q), p_addr = smem_u32(smem + AF2_SMEM_P);
+            auto issue_s = [&](int j) {
+                const int s = j % NS;
+                const int valid = min(AF_BKV, a.N - j * AF_BKV);
+                const int ncols = (valid + 15) & ~15;
+                mbar_wait(&k_full[s], (j / NS) & 1);
+                if (j > 0) mbar_wait(s_free, (j - 1) & 1);
+                tc_fence_after_sync();
+                const uint32_t idesc = make_idesc_bf16(128, ncols, 0, 0);
+                const uint64_t adesc = make_smem_desc_sw128(q_addr, 0, 1024);
+                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + AF2_SMEM_K + s * AF_KVTILE), 0, 1024);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_s, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
+                umma_commit(s_full);
+            };
+            VITK_TRACE_EV(a.trace, 1);
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            VITK_TRACE_EV(a.trace, 2);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1, ks = j % NS;
+                if (j + 1 < nkv) issue_s(j + 1);
+                const int valid = min(AF_BKV, a.N - j * AF_BKV);
+                const int ksteps = (valid + 15) >> 4;
+                mbar_wait(&v_full[ks], (j / NS) & 1);
+                // O_g[128, HD] += P_j[128, 32g..32g+31] * V_j[32g..32g+31, HD]: A = P (K-major), B = V read MN-major
+                constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, 0, 1);
+                const uint32_t v_addr = smem_u32(smem + AF2_SMEM_V + ks * AF_KVTILE);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    mbar_wait(&p_full[2 * g + s], (j >> 1) & 1);
+                    tc_fence_after_sync();
+                    for (int k = 2 * g; k < ksteps && k < 2 * g + 2; ++k) {
+                        const uint64_t adesc = make_smem_desc_sw128(p_addr + s * AF_QTILE + k * 32, 0, 1024);
+                        const uint64_t bdesc = make_smem_desc_sw128(v_addr + k * 2048, AF_BKV * 128, 1024);
+                        umma_bf16(tmem_o + 64 * g, adesc, bdesc, idesc_pv, (j > 0 || k > 2 * g) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&o_full[s]);
+                umma_commit(&kv_empty[ks]);
+                if (j < 8) VITK_TRACE_EV(a.trace, 8 + j);
+            }
+        }
+    } else {
+        // ===================== softmax: group g, thread == query row =====================
+        const int g = warp >> 2, wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const uint32_t lane_off = uint32_t(wq * 32) << 16;
+        const uint32_t tmem_og = tmem_o + 64 * g;
+        const bool warp_live = (q0 + wq * 32) < a.N;   // warp-uniform: at least one real query row in this warp
+        float m_ref = -INFINITY, l_run = 0.f;
+        const int sw = row & 7;
+
+        for (int j = 0; j < nkv; ++j) {
+            const int valid = min(AF_BKV, a.N - j * AF_BKV);
+            const int nv = min(32, valid - 32 * g);       // valid columns of this group in tile j (may be <= 0)
+            const bool work = warp_live && nv > 0;        // warp-uniform
+            mbar_wait(s_full, j & 1);
+            tc_fence_after_sync();
+            if (threadIdx.x == 0 && j < 8) VITK_TRACE_EV(a.trace, 24 + 2 * j);
+            uint32_t sr[32];
+            if (work) {
+                tmem_ld_32x32b_x32(tmem_s + lane_off + 32 * g, sr);
+                tmem_ld_wait();
+            }
+            tc_fence_before_sync();
+            mbar_arrive(s_free);
+            if (work) {
+                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                if (nv == 32) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sr[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        mx4[i & 3] = fmaxf(mx4[i & 3], (i < nv) ? __uint_as_float(sr[i]) : -INFINITY);
+                }
+                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+                const float mxs = mx * a.scale_log2;
+                if (j == 0) {
+                    m_ref = mxs;    // (a group with no valid column in tile 0 has none in any tile)
+                } else if (__any_sync(0xffffffffu, mxs > m_ref + AF_RESCALE_TAU)) {
+                    // lazy rescale (warp-uniform branch): raise the reference maximum, rescale l and O_g in TMEM
+                    mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);   // PV_{j-1} has landed
+                    tc_fence_after_sync();
+                    const float m_new = fmaxf(m_ref, mxs);
+                    const float alpha = ex2_approx(m_ref - m_new);
+                    l_run *= alpha;
+                    m_ref = m_new;
+#pragma unroll
+                    for (int c = 0; c < HD / 16; ++c) {
+                        uint32_t r[16];
+                        tmem_ld_32x32b_x16(tmem_og + lane_off + c * 16, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                        tmem_st_32x32b_x16(tmem_og + lane_off + c * 16, r);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before_sync();
+                }
+                // P buffer (j & 1) was last read by PV_{j-2}
+                if (j >= 2) mbar_wait(&o_full[j & 1], ((j - 2) >> 1) & 1);
+                uint8_t* p_row = smem + AF2_SMEM_P + (j & 1) * AF_QTILE + row * 128;
+                float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+                const float nm = -m_ref;
+                if (nv == 32) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float p[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            p[i] = ex2_approx(fmaf(__uint_as_float(sr[u * 8 + i]), a.scale_log2, nm));
+                            ps4[i & 3] += p[i];
+                        }
+                        *reinterpret_cast<uint4*>(p_row + (((4 * g + u) ^ sw) << 4)) = make_uint4(
+                            pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (u < ((nv + 15) >> 4) * 2) {   // 16-byte units of 8 columns that the PV MMA may read
+                            float p[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float v = ex2_approx(fmaf(__uint_as_float(sr[u * 8 + i]), a.scale_log2, nm));
+                                p[i] = (u * 8 + i < nv) ? v : 0.f;
+                                ps4[i & 3] += p[i];
+                            }
+                            *reinterpret_cast<uint4*>(p_row + (((4 * g + u) ^ sw) << 4)) = make_uint4(
+                                pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]),
+                                pack_bf16(p[6], p[7]));
+                        }
+                    }
+                }
+                l_run += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+                fence_proxy_async_smem();
+            }
+            mbar_arrive(&p_full[2 * g + (j & 1)]);
+            if (threadIdx.x == 0 && j < 8) VITK_TRACE_EV(a.trace, 25 + 2 * j);
+        }
+        // merge the two groups' partial softmax states, then each group writes half of the head's columns
+        // (the Q tile is dead: its last reader, S of the last tile, completed before this group's last s_full wait)
+        float2* stat = reinterpret_cast<float2*>(smem + AF2_SMEM_Q);
+        stat[g * 128 + row] = make_float2(m_ref, l_run);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp_live) {
+            const float2 other = stat[(g ^ 1) * 128 + row];
+            const float m0 = g ? other.x : m_ref, l0 = g ? other.y : l_run;
+            const float m1 = g ? m_ref : other.x, l1 = g ? l_run : other.y;
+            const float m = fmaxf(m0, m1);
+            const bool has1 = a.N > 32;                     // group 1 saw at least one key: O_1 holds data
+            const float w0 = ex2_approx(m0 - m);
+            const float w1 = has1 ? ex2_approx(m1 - m) : 0.f;
+            const float l = l0 * w0 + l1 * w1;
+            const float inv = 1.0f / l;
+            const float c0 = w0 * inv, c1 = w1 * inv;
+            mbar_wait(&o_full[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
+            tc_fence_after_sync();
+            if (threadIdx.x == 0) VITK_TRACE_EV(a.trace, 60);
+            const int n = q0 + row;
+            __nv_bfloat16* dst = a.out + ((long long)b * a.N + n) * a.D + h * HD;
+            // d = 64: the tile leaves through a swizzled staging tile (P buffer 0, free once the last PV has completed)
+            // and ONE TMA store; d = 48: direct 16-byte stores
+            uint8_t* stage_row = smem + AF2_SMEM_P + row * 128;
+#pragma unroll
+            for (int c = 0; c < HD / 16; ++c) {
+                if ((c & 1) != g) continue;
+                uint32_t r0[16], r1[16];
+                tmem_ld_32x32b_x16(tmem_o + lane_off + c * 16, r0);             // warp-collective
+                if (has1) tmem_ld_32x32b_x16(tmem_o + 64 + lane_off + c * 16, r1);
+                tmem_ld_wait();
+                float f[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    f[i] = has1 ? fmaf(__uint_as_float(r1[i]), c1, __uint_as_float(r0[i]) * c0)
+                                : __uint_as_float(r0[i]) * c0;
+                const uint4 lo = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                            pack_bf16(f[6], f[7]));
+                const uint4 hi = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
+                                            pack_bf16(f[14], f[15]));
+                if constexpr (HD == 64) {
+                    *reinterpret_cast<uint4*>(stage_row + (((2 * c) ^ sw) << 4)) = lo;
+                    *reinterpret_cast<uint4*>(stage_row + (((2 * c + 1) ^ sw) << 4)) = hi;
+                } else if (n < a.N) {
+                    st_v4(dst + c * 16, lo);
+                    st_v4(dst + c * 16 + 8, hi);
+                }
+            }
+            if (g == 0 && n < a.N) a.lse2[((long long)b * a.H + h) * a.N + n] = m + log2f(l);
+            if constexpr (HD == 64) fence_proxy_async_smem();
+        }
+        if constexpr (HD == 64) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 0) {
+                tma_store_3d(&tmO, smem + AF2_SMEM_P, h * HD, q0, b);   // rows >= N are clipped by the map
+                tma_store_commit();
+                tma_store_wait_read<0>();
+            }
+        }
+        if (threadIdx.x == 0) VITK_TRACE_EV(a.trace, 61);
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after_sync();
+        tmem_dealloc<AF2_TMEM_COLS>(tmem_base);
+    }
+}
+
 // 2-D map over a token-major bf16 tensor viewed as [B*N rows, G*d columns] (G = 3H for qkv, H for O / dO), box
 // {64 columns, box_rows}. Rank-2 boxes are markedly cheaper for the TMA unit than the rank-4 {d, G, N, B} form; the
 // price is that a tile may run past its image into the next one (rows) or the next head (columns, d = 48): every
@@ -281,6 +589,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // of the tensor are zero-filled by TMA.
 int make_tok_tmap2d(CUtensorMap* out, const void* p, long long rows, long long cols, int box_rows) {
     return make_tmap_2d_bf16(out, p, (uint64_t)cols, (uint64_t)rows, (uint64_t)cols, 64, (uint32_t)box_rows);
+}
+
+// VITK_ATTN_WG2=0 selects the one-group kernels (A/B runs); read on every call so a process can time both.
+bool attn_two_groups() {
+    const char* e = getenv("VITK_ATTN_WG2");
+    return !(e && e[0] == '0');
 }
 
 template <int HD>
@@ -297,7 +611,20 @@ static int launch_attn_fwd(const void* qkv, const AttnFwdArgs& a, int B, int N, 
         attr = true;
     }
     dim3 grid((N + AF_BQ - 1) / AF_BQ, H, B);
-    attn_fwd_kernel<HD><<<grid, AF_THREADS, AF_SMEM_BYTES, st>>>(tmq, tmkv, a);
+    if (attn_two_groups()) {
+        CUtensorMap tmo;
+        if (make_tmap_3d_tok_store(&tmo, a.out, (uint64_t)H * d, (uint64_t)N, (uint64_t)B, 128)) return VITK_ERR_TMAP;
+        static bool attr2 = false;
+        if (!attr2) {
+            if (cudaFuncSetAttribute(attn_fwd2_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     AF2_SMEM_BYTES) != cudaSuccess)
+                return VITK_ERR_CUDA;
+            attr2 = true;
+        }
+        attn_fwd2_kernel<HD><<<grid, AF2_THREADS, AF2_SMEM_BYTES, st>>>(tmq, tmkv, tmo, a);
+    } else {
+        attn_fwd_kernel<HD><<<grid, AF_THREADS, AF_SMEM_BYTES, st>>>(tmq, tmkv, a);
+    }
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
 }
 
@@ -313,7 +640,19 @@ extern "C" int vitk_attn_fwd(const void* qkv_bf16, void* out_bf16, float* lse2, 
     a.scale_log2 = scale * 1.4426950408889634f;
     a.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
     a.lse2 = lse2;
+    a.trace = nullptr;
+#ifdef VITK_TRACE
+    a.trace = g_attn_trace;
+#endif
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (d == 64) return launch_attn_fwd<64>(qkv_bf16, a, B, N, H, d, st);
     return launch_attn_fwd<48>(qkv_bf16, a, B, N, H, d, st);
 }
+
+#ifdef VITK_TRACE
+// instrumented build only: device buffer of int64 [n_ctas * 64] that the attention kernels fill with SM clocks
+extern "C" int vitk_debug_set_trace(void* p) {
+    g_attn_trace = reinterpret_cast<long long*>(p);
+    return VITK_OK;
+}
+#endif

@@ -266,6 +266,12 @@ __device__ __forceinline__ void tma_store_2d_s(const CUtensorMap* m, uint32_t sr
                  "r"(src_saddr), "r"(c0), "r"(c1)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
@@ -504,5 +510,19 @@ __device__ __forceinline__ int warp_colsum16_col(int lane) {
     return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
+
+// ---- optional per-CTA event trace (instrumented build only: -DVITK_TRACE, scripts/trace_attn.py) ----
+// trace[cta * 64 + id] = SM clock at event `id`; all roles of a CTA share one SM clock, so differences are cycles.
+#ifdef VITK_TRACE
+__device__ __forceinline__ void trace_ev(long long* trace, int id) {
+    if (trace != nullptr) {
+        const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        if (cta < 16384u) trace[cta * 64 + id] = clock64();
+    }
+}
+#define VITK_TRACE_EV(ptr, id) trace_ev((ptr), (id))
+#else
+#define VITK_TRACE_EV(ptr, id) ((void)0)
+#endif
 
 }  // namespace vitk

@@ -108,6 +108,15 @@ inline int make_tmap_2d_store(CUtensorMap* out, const void* ptr, int elem_bytes,
                      elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
 }
 
+// 3-D bf16 map over a token-major [B, N, cols] OUTPUT for TMA stores of one image's [box_rows x 64 columns] SWIZZLE_128B
+// tile: rows past the end of the image (>= N) are clipped by the map instead of landing in the next image.
+inline int make_tmap_3d_tok_store(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t N, uint64_t B,
+                                  uint32_t box_rows) {
+    uint64_t dims[3] = {cols, N, B};
+    uint64_t strides[2] = {cols * 2, cols * N * 2};
+    uint32_t box[3] = {64, box_rows, 1};
+    return make_tmap(out, ptr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+}
 // 4-D bf16 map over a batched row-major operand: logical dims (inner | rows, batch_h, batch_b) with element strides
 // (1 | pitch, stride_h, stride_b). The three outer dims are emitted in order of increasing stride (the driver wants
 // each stride to be a multiple of the previous one); perm[i] tells the kernel which logical coordinate
