@@ -17,7 +17,7 @@ def timeit(fn, iters=10, warm=3):
     return s.elapsed_time(e) / iters * 1e-3
 
 rows = []
-tag = "wg2" if os.environ.get("VITK_ATTN_WG2", "1") != "0" else "wg1"
+tag = "v" + os.environ.get("VITK_ATTN_WG2", "1")
 for (B, N, H, d) in [(2, 197, 6, 64), (128, 197, 12, 64), (64, 785, 12, 64), (128, 196, 8, 48)]:
     qkv = torch.randn(B * N, 3 * H * d, device=dev).bfloat16()
     do = torch.randn(B * N, H * d, device=dev).bfloat16()

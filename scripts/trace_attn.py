@@ -40,6 +40,8 @@ t0 = t[:, 0]
 span = (t[:, 61].max() - t0.min()).item()   # (different SMs: clocks are only roughly aligned)
 def stat(name, a, b):
     m = (t[:, a] > 0) & (t[:, b] > 0)
+    if int(m.sum()) == 0:
+        return
     dlt = (t[m, b] - t[m, a])
     print(f"  {name:44s} mean {dlt.mean().item():8.0f}  median {dlt.median().item():8.0f}  p90 {dlt.quantile(0.9).item():8.0f}  (n={int(m.sum())})")
 print(f"{which} B{B} N{N} H{H} d{d}: {ncta} CTAs, clocks (SM cycles)")

@@ -24,13 +24,13 @@ CASES = [(2, 197, 6, 64), (1, 128, 1, 64), (3, 37, 2, 64), (2, 785, 3, 64), (2, 
          (1, 1297, 2, 64), (2, 198, 3, 64), (4, 256, 2, 64), (2, 1, 2, 64)]
 
 
-@pytest.mark.parametrize("groups", [2, 1])
-@pytest.mark.parametrize("B,N,H,d", CASES)
-def test_attn_fwd(B, N, H, d, groups, monkeypatch):
-    """groups=2: eight softmax warps per CTA, two independent online softmaxes merged per row (default);
-    groups=1: the four-warp kernel (VITK_ATTN_WG2=0)."""
+@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("B,N,H,d", CASES + [(40, 197, 12, 64), (9, 300, 4, 48)])
+def test_attn_fwd(B, N, H, d, variant, monkeypatch):
+    """VITK_ATTN_WG2 = 1 (default): eight softmax warps per CTA, two online softmaxes merged per row; 0: the first
+    kernel (four softmax warps)."""
     from vit_torch_b200 import ops
-    monkeypatch.setenv("VITK_ATTN_WG2", "1" if groups == 2 else "0")
+    monkeypatch.setenv("VITK_ATTN_WG2", str(variant))
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + N)
     qkv = (torch.randn((B * N, 3 * H * d), device="cuda", generator=g) * 1.5).to(torch.bfloat16)
     scale = d ** -0.5

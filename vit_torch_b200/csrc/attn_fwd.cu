@@ -592,6 +592,7 @@ int make_tok_tmap2d(CUtensorMap* out, const void* p, long long rows, long long c
 }
 
 // VITK_ATTN_WG2=0 selects the one-group kernels (A/B runs); read on every call so a process can time both.
+// VITK_ATTN_WG2=0 selects the one-group kernels (A/B runs); read on every call so a process can time both.
 bool attn_two_groups() {
     const char* e = getenv("VITK_ATTN_WG2");
     return !(e && e[0] == '0');
