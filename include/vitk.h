@@ -108,6 +108,14 @@ int vitk_layernorm_bwd_ex(const void* dy, int dy_is_f32, const float* x, long lo
                           void* dx_bf16, const float* colscale, float* dweight, float* dbias, float* dxsum,
                           long long rows, int D, void* stream);
 
+/* Fused mean softmax cross-entropy + its gradient + argmax accuracy of logits fp32 [rows, C] (row pitch ld), labels
+ * int64 [rows]: out2[0] = mean loss, out2[1] = number of rows whose first-maximum column equals the label (as a float),
+ * dlogits (optional, row pitch ldd) = (softmax - onehot) / rows. Deterministic, no host synchronisation. Replaces
+ * nn.CrossEntropyLoss + autograd (utils_network.py:429-433, main.py:244) and classification_count_correct
+ * (utils_network.py:85-95). */
+int vitk_cross_entropy(const float* logits, long long ld, const long long* labels, int rows, int C, float* out2,
+                       float* dlogits, long long ldd, void* stream);
+
 /* out[c] += sum_r x[r*ldx + c], fp32 (d_pos = sum_b dX[b,:,:], d_cls; SURVEY App. A.3 token assembly). cols % 4 == 0. */
 int vitk_colsum_f32(const float* x, long long ldx, long long rows, long long cols, float* out, void* stream);
 

@@ -1,19 +1,13 @@
 #!/bin/bash
-# Round profile pass (run under gpurun, one GPU): bench line, ncu launch list of the same command, per-launch DRAM
-# traffic of every GEMM launch of one step, and one --set full capture of the top kernels.
+# Round profile pass (run under gpurun, one GPU): bench line, ncu launch list of the same command, and one --set full
+# capture of each attention kernel. (GEMM traffic / GEMM and LayerNorm captures: scripts/gpu_profile_gemm.sh.)
 set -u
 mkdir -p gpurun_out
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r01.json 2> gpurun_out/bench_r01.err; echo "bench rc=$?"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r01_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:gemm \
-    -s 438 -c 146 --csv --log-file gpurun_out/r01_gemm_traffic.csv \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_traffic.log 2>&1; echo "ncu traffic rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:gemm2_bf16 -s 2 -c 1 -o gpurun_out/r01_gemm2_fc1_gelu -f \
-    python scripts/prof_gemm.py gelu 3072 768 > /dev/null 2>&1; echo "ncu full gelu rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:gemm2_bf16 -s 2 -c 1 -o gpurun_out/r01_gemm2_qkv_fwd -f \
-    python scripts/prof_gemm.py fwd 2304 768 > /dev/null 2>&1; echo "ncu full fwd rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:attn_bwd_dkv -s 1 -c 1 -o gpurun_out/r01_attn_bwd_dkv -f \
-    python scripts/prof_attn.py > /dev/null 2>&1; echo "ncu full attn rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:ln_bwd -s 1 -c 1 -o gpurun_out/r01_ln_bwd -f \
-    python scripts/prof_attn.py ln > /dev/null 2>&1; echo "ncu full ln rc=$?"
+python scripts/prof_attn.py > /dev/null 2>&1; echo "plain attn rc=$?"
+for k in attn_fwd2 attn_bwd_dq2 attn_bwd_dkv2; do
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -o gpurun_out/r01_$k -f \
+      python scripts/prof_attn.py > /dev/null 2>&1; echo "ncu full $k rc=$?"
+done

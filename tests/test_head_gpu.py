@@ -31,3 +31,27 @@ def test_head_matches_torch(B, fin, units):
     assert nerr(xo.grad, xr.grad) <= 2e-2
     for (k, p), (_, q) in zip(head.named_parameters(), ref.named_parameters()):
         assert nerr(p.grad, q.grad) <= 2e-2, k
+
+
+@pytest.mark.parametrize("B,C,pitch", [(128, 10, 16), (512, 10, 10), (7, 1000, 1000), (1, 3, 8), (33, 37, 40)])
+def test_fused_cross_entropy_matches_torch(B, C, pitch):
+    """vitk_cross_entropy (loss + gradient + argmax count in one launch) vs nn.CrossEntropyLoss + autograd and
+    classification_count_correct (utils_network.py:85-95, 429-433). fp32 glue tolerance 1e-4."""
+    from vit_torch_b200 import functional
+    g = torch.Generator(device="cuda").manual_seed(B * 31 + C)
+    buf = torch.randn((B, pitch), device="cuda", generator=g) * 3
+    logits = buf[:, :C].detach().requires_grad_(True)           # strided rows, like the padded head output
+    labels = torch.randint(0, C, (B,), device="cuda", generator=g)
+    if B > 2:
+        logits.data[1, :] = 0.5                                  # ties: argmax must pick the first maximum
+    loss, ncorrect = functional.cross_entropy(logits, labels)
+    (loss * 2.0).backward()
+    ref_in = buf[:, :C].detach().clone().requires_grad_(True)
+    if B > 2:
+        ref_in.data[1, :] = 0.5
+    ref = torch.nn.functional.cross_entropy(ref_in, labels)
+    (ref * 2.0).backward()
+    assert abs(loss.item() - ref.item()) <= 1e-4 * max(1.0, abs(ref.item()))
+    assert (logits.grad - ref_in.grad).abs().max().item() <= 1e-6 + 1e-4 * ref_in.grad.abs().max().item()
+    assert int(ncorrect.item()) == int((ref_in.argmax(1) == labels).sum().item())
+    assert not ncorrect.requires_grad

@@ -32,6 +32,7 @@ SIGNATURES = {
     "vitk_layernorm_fwd_ex": [_P, _L, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
     "vitk_layernorm_bwd_ex": [_P, _I, _P, _L, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _L, _I, _P],
     "vitk_colsum_f32": [_P, _L, _L, _L, _P, _P],
+    "vitk_cross_entropy": [_P, _L, _P, _I, _I, _P, _P, _L, _P],
     "vitk_colsum_prod": [_P, _L, _P, _L, _L, _I, _P, _P],
     "vitk_scale_cast": [_P, _L, _L, _L, _I, _P, _P, _L, _P, _P],
     "vitk_patchify": [_P, _P, _I, _I, _I, _I, _I, _P],

@@ -579,6 +579,64 @@ static inline int ln_grid(long long rows) {
     return (int)(need < cap ? need : cap);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fused softmax cross-entropy (mean) + gradient + argmax accuracy of one batch of logits: replaces CrossEntropyLoss
+// (utils_network.py:429-433, created main.py:244), its autograd and classification_count_correct
+// (utils_network.py:85-95) without a host synchronisation. One CTA, one warp per row (round-robin); the per-warp
+// partial losses are combined in a fixed order, so the result is deterministic.
+//   out[0] = mean_r (logsumexp(x_r) - x_r[label_r]);  out[1] = #(argmax_c x_r[c] == label_r) (first maximum, as
+//   torch.argmax);  dlogits[r, c] = (softmax(x_r)[c] - [c == label_r]) / rows
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+cross_entropy_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ labels, int rows,
+                     int C, float* __restrict__ out, float* __restrict__ dlogits, long long ldd) {
+    __shared__ float s_loss[32];
+    __shared__ int s_correct[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const float inv_rows = 1.0f / (float)rows;
+    float loss = 0.f;
+    int correct = 0;
+    for (int r = warp; r < rows; r += nwarps) {
+        const float* x = logits + (long long)r * ld;
+        const int label = (int)labels[r];
+        float mx = -INFINITY;
+        int arg = 0x7fffffff;
+        for (int c = lane; c < C; c += 32) {
+            const float v = x[c];
+            if (v > mx) { mx = v; arg = c; }   // strict: keeps the first maximum of this lane's columns
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+        }
+        float sum = 0.f;
+        for (int c = lane; c < C; c += 32) sum += __expf(x[c] - mx);
+        sum = warp_sum(sum);
+        const float lse = mx + __logf(sum);
+        const float inv = 1.0f / sum;
+        if (dlogits != nullptr) {
+            float* d = dlogits + (long long)r * ldd;
+            for (int c = lane; c < C; c += 32)
+                d[c] = (__expf(x[c] - mx) * inv - (c == label ? 1.0f : 0.0f)) * inv_rows;
+        }
+        if (lane == 0) {
+            loss += lse - ((label >= 0 && label < C) ? x[label] : 0.f);
+            correct += (arg == label) ? 1 : 0;
+        }
+    }
+    if (lane == 0) { s_loss[warp] = loss; s_correct[warp] = correct; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tl = 0.f;
+        int tc = 0;
+        for (int w = 0; w < nwarps; ++w) { tl += s_loss[w]; tc += s_correct[w]; }
+        out[0] = tl * inv_rows;
+        out[1] = (float)tc;
+    }
+}
+
 }  // namespace vitk
 
 using namespace vitk;
@@ -732,6 +790,15 @@ extern "C" int vitk_cast_f32_bf16(const float* x, void* y_bf16, long long n, voi
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     cast_f32_bf16_kernel<<<(int)blocks, 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(y_bf16), n);
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
+extern "C" int vitk_cross_entropy(const float* logits, long long ld, const long long* labels, int rows, int C,
+                                  float* out2, float* dlogits, long long ldd, void* stream) {
+    if (rows <= 0 || C <= 0 || ld < C || !logits || !labels || !out2 || (dlogits && ldd < C)) return VITK_ERR_ARG;
+    int threads = rows >= 32 ? 1024 : rows * 32;
+    cross_entropy_kernel<<<1, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, ld, labels, rows, C, out2,
+                                                                                     dlogits, ldd);
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
 }
 

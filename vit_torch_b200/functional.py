@@ -526,3 +526,28 @@ class HeadFn(torch.autograd.Function):
                 ops.gemm(dyv, w, b_mn=True, K=n_out, epilogue=ops.EPI_STORE_F32, out=dx)
                 return (dx, None, *grads)
         return (None, None, *grads)
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """nn.CrossEntropyLoss() (mean) of utils_network.py:429-433 as one kernel that also produces the gradient and the
+    argmax-accuracy count of utils_network.py:85-95. Returns (loss, n_correct) as 0-d device tensors (no host sync);
+    n_correct carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        out2, dl = ops.cross_entropy(logits, labels, want_grad=ctx.needs_input_grad[0])
+        if dl is not None:
+            ctx.save_for_backward(dl)
+        ncorrect = out2[1]
+        ctx.mark_non_differentiable(ncorrect)
+        return out2[0], ncorrect
+
+    @staticmethod
+    def backward(ctx, dloss, _dcorrect):
+        (dl,) = ctx.saved_tensors
+        return dl * dloss, None
+
+
+def cross_entropy(logits, labels):
+    """(mean cross-entropy, number of correct argmax predictions): fused drop-in for the reference's loss + accuracy."""
+    return CrossEntropyFn.apply(logits, labels)

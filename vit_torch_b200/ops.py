@@ -232,6 +232,23 @@ def colsum_f32_accum(x, ldx, rows, cols, out):
     launch_count += 1
 
 
+def cross_entropy(logits, labels, want_grad=True):
+    """logits fp32 [B, C] (rows may be strided), labels int64 [B] -> (out2 fp32 [2] = (mean loss, #correct),
+    dlogits fp32 [B, C] = d(mean loss)/d(logits) or None). One launch, no host sync."""
+    global launch_count
+    _need_cuda(logits, labels)
+    assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    assert labels.dtype == torch.int64 and labels.is_contiguous() and labels.numel() == logits.shape[0]
+    B, C = logits.shape
+    out2 = torch.empty((2,), dtype=torch.float32, device=logits.device)
+    dl = torch.empty((B, C), dtype=torch.float32, device=logits.device) if want_grad else None
+    lib = _lib.load()
+    check(lib.vitk_cross_entropy(ptr(logits), logits.stride(0), ptr(labels), B, C, ptr(out2), ptr(dl), C, _stream()),
+          "vitk_cross_entropy")
+    launch_count += 1
+    return out2, dl
+
+
 def colsum_prod_accum(a, b, out):
     """out[N] += sum_r a_f32[r, :] * b_bf16[r, :]."""
     global launch_count

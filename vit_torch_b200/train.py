@@ -114,10 +114,17 @@ class Trainer:
         self._sx = self._sy = self._sloss = None
         self._eager_steps = 0
         self.launches_per_step = None   # libvitk launches inside one captured step
+        self.last_correct = None        # 0-d device tensor: correct argmax predictions of the last step's batch
 
     def _step_eager(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         out = self.model(x)
-        loss = F.cross_entropy(out, y)
+        if out.dim() == 2 and out.dtype == torch.float32 and out.stride(1) == 1 and y.dtype == torch.int64:
+            # fused loss + gradient + argmax-accuracy count (utils_network.py:85-95, 429-433), no host sync
+            from . import functional
+            loss, self.last_correct = functional.cross_entropy(out, y)
+        else:   # e.g. soft / non-int64 targets: torch's loss (still on the GPU)
+            loss = F.cross_entropy(out, y)
+            self.last_correct = None
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
         if self.reducer is not None:
