@@ -208,6 +208,9 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-sync-read", action="store_true",
+                    help="e2e: read each step's loss with a blocking .item() right after enqueueing it (A/B; default: "
+                         "the read of step i happens after step i+1 has been enqueued)")
     ap.add_argument("--no-overlap", action="store_true", help="DP: all-reduce after backward instead of overlapped")
     ap.add_argument("--nccl-ctas", type=int, default=4,
                     help="DP: thread blocks left to the overlapped NCCL all-reduce (0 = NCCL default, GEMMs use every SM)")
@@ -258,12 +261,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, steps):
+    def timed(step_fn, steps, finish=None):
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(steps):
             out = step_fn()
+        if finish is not None:
+            out = finish()
         e.record()
         barrier()
         ms = s.elapsed_time(e)
@@ -278,12 +283,24 @@ def main():
 
     # e2e input pipeline: every step's batch goes pinned host -> device inside the timed region, on a copy stream so
     # that the transfer of batch i+1 overlaps step i (what DataLoader(pin_memory=True) + non_blocking copies give the
-    # reference loop, utils_network.py:409-410); the step waits on the copy's event, the loss is read back every step.
+    # reference loop, utils_network.py:409-410); the step waits on the copy's event. Every step's loss is read back
+    # on the host inside the timed region: step i's value travels through a pinned buffer and is read right after
+    # step i+1 has been enqueued (the last one before the closing event), so the GPU never idles behind the read.
     copy_stream = torch.cuda.Stream()
     stage_x = [torch.empty_like(x_dev) for _ in range(2)]
     stage_y = [torch.empty_like(y_dev) for _ in range(2)]
     stage_ev = [torch.cuda.Event() for _ in range(2)]
-    e2e_state = {"it": 0, "primed": False}
+    e2e_state = {"it": 0, "primed": False, "pending": None, "losses": []}
+    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+
+    def read_pending():
+        k = e2e_state["pending"]
+        if k is not None:
+            loss_ev[k].synchronize()
+            e2e_state["losses"].append(float(loss_host[k]))      # device -> host read of the step result
+            e2e_state["pending"] = None
+        return e2e_state["losses"][-1] if e2e_state["losses"] else None
 
     def prefetch(k):
         copy_stream.wait_stream(torch.cuda.current_stream())   # the buffer's previous consumer has been enqueued
@@ -307,8 +324,14 @@ def main():
         else:
             prefetch(k ^ 1)
             loss = trainer.step(stage_x[k], stage_y[k])
+        loss_host[k].copy_(loss, non_blocking=True)
+        loss_ev[k].record()
+        read_pending()                                    # the previous step's loss (this step is already enqueued)
+        e2e_state["pending"] = k
+        if args.e2e_sync_read:
+            read_pending()
         e2e_state["it"] += 1
-        return loss.item()                                # device -> host read of the step result
+        return None
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -326,14 +349,27 @@ def main():
 
     e2e = None
     if not args.no_e2e:
+        # stand-alone rate of the pinned host -> device copy on this box (reported next to e2e: when it is low, the
+        # transfer of batch i+1 no longer hides completely behind step i)
+        hs, he = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        hs.record()
+        stage_x[0].copy_(x_host, non_blocking=True)
+        he.record()
+        torch.cuda.synchronize()
+        h2d_gbs = x_host.numel() * 4 / (hs.elapsed_time(he) * 1e-3) / 1e9
         for _ in range(2):
             step_e2e()
+        read_pending()
         torch.cuda.synchronize()
         e2e_state["primed"] = False                       # the first timed step issues its own H2D copy
-        ms_e, _ = timed(step_e2e, args.steps)
+        e2e_state["losses"] = []
+        ms_e, _ = timed(step_e2e, args.steps, finish=read_pending)
+        assert len(e2e_state["losses"]) == args.steps     # every step's loss reached the host inside the timed region
         e2e = {"value": world * bs * args.steps / (ms_e * 1e-3), "unit": "images/s",
                "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4,
-               "ms_per_step": ms_e / args.steps}
+               "ms_per_step": ms_e / args.steps, "last_loss": e2e_state["losses"][-1],
+               "h2d_gbs_standalone": h2d_gbs}
 
     # roofline of the dominant kernel family (tcgen05 GEMM): CUDA events around every GEMM launch of the same loop
     pk = peaks()

@@ -557,7 +557,7 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
         if (lane == 0) {
             for (int j = NS; j < nkv; ++j) {   // the first NS tiles were issued in the prologue
                 const int s = j % NS;
-                mbar_wait(&kv_empty[s], ((j / NS) & 1) ^ 1);
+                mbar_wait_backoff(&kv_empty[s], ((j / NS) & 1) ^ 1);
                 mbar_expect_tx(&kv_full[s], 2 * AB_T64);
                 tma_load_2d(smem + DQ2_SMEM_K + s * AB_T64, &tmQKV64, &kv_full[s], (a.H + h) * HD, b * a.N + j * 64);
                 tma_load_2d(smem + DQ2_SMEM_V + s * AB_T64, &tmQKV64, &kv_full[s], (2 * a.H + h) * HD, b * a.N + j * 64);
@@ -571,8 +571,8 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
                 const int s = j % NS;
                 const int valid = min(64, a.N - j * 64);
                 const uint32_t idesc = make_idesc_bf16(128, (valid + 15) & ~15, 0, 0);
-                mbar_wait(&kv_full[s], (j / NS) & 1);
-                if (j > 0) mbar_wait(sdp_free, (j - 1) & 1);
+                mbar_wait_backoff(&kv_full[s], (j / NS) & 1);
+                if (j > 0) mbar_wait_backoff(sdp_free, (j - 1) & 1);
                 tc_fence_after_sync();
                 const uint64_t qd = make_smem_desc_sw128(q_addr, 0, 1024);
                 const uint64_t dod = make_smem_desc_sw128(do_addr, 0, 1024);
@@ -585,7 +585,7 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
                 umma_commit(sdp_full);
             };
             VITK_TRACE_EV(a.trace, 1);
-            mbar_wait(qdo_full, 0);
+            mbar_wait_backoff(qdo_full, 0);
             issue_sdp(0);
             VITK_TRACE_EV(a.trace, 2);
             for (int j = 0; j < nkv; ++j) {
@@ -593,7 +593,7 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
                 if (j + 1 < nkv) issue_sdp(j + 1);
                 const int valid = min(64, a.N - j * 64);
                 const int ksteps = (valid + 15) >> 4;
-                mbar_wait(ds_full, j & 1);
+                mbar_wait_backoff(ds_full, j & 1);
                 tc_fence_after_sync();
                 constexpr uint32_t idesc_dq = make_idesc_bf16(128, HD, 0, 1);
                 const uint32_t k_addr = smem_u32(smem + DQ2_SMEM_K + s * AB_T64);
@@ -802,7 +802,7 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
         if (lane == 0) {
             for (int i = NS; i < nq; ++i) {   // the first NS tiles were issued in the prologue
                 const int s = i % NS;
-                mbar_wait(&qdo_empty[s], ((i / NS) & 1) ^ 1);
+                mbar_wait_backoff(&qdo_empty[s], ((i / NS) & 1) ^ 1);
                 mbar_expect_tx(&qdo_full[s], 2 * AB_T64);
                 tma_load_2d(smem + DKV2_SMEM_Q + s * AB_T64, &tmQKV64, &qdo_full[s], h * HD, b * a.N + i * 64);
                 tma_load_2d(smem + DKV2_SMEM_DO + s * AB_T64, &tmDO64, &qdo_full[s], h * HD, b * a.N + i * 64);
@@ -816,8 +816,8 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
                 const int s = i % NS;
                 const int valid = min(64, a.N - i * 64);
                 const uint32_t idesc = make_idesc_bf16(128, (valid + 15) & ~15, 0, 0);
-                mbar_wait(&qdo_full[s], (i / NS) & 1);
-                if (i > 0) mbar_wait(st_free, (i - 1) & 1);
+                mbar_wait_backoff(&qdo_full[s], (i / NS) & 1);
+                if (i > 0) mbar_wait_backoff(st_free, (i - 1) & 1);
                 tc_fence_after_sync();
                 const uint64_t kd = make_smem_desc_sw128(k_addr, 0, 1024);
                 const uint64_t vd = make_smem_desc_sw128(v_addr, 0, 1024);
@@ -830,7 +830,7 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
                 umma_commit(st_full);
             };
             VITK_TRACE_EV(a.trace, 1);
-            mbar_wait(kv_full, 0);
+            mbar_wait_backoff(kv_full, 0);
             issue_st(0);
             VITK_TRACE_EV(a.trace, 2);
             for (int i = 0; i < nq; ++i) {
@@ -838,7 +838,7 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
                 if (i + 1 < nq) issue_st(i + 1);
                 const int valid = min(64, a.N - i * 64);
                 const int ksteps = (valid + 15) >> 4;
-                mbar_wait(pds_full, i & 1);
+                mbar_wait_backoff(pds_full, i & 1);
                 tc_fence_after_sync();
                 constexpr uint32_t idesc_acc = make_idesc_bf16(128, HD, 0, 1);
                 const uint32_t q_addr = smem_u32(smem + DKV2_SMEM_Q + s * AB_T64);

@@ -360,7 +360,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (lane == 0) {
             for (int j = NS; j < nkv; ++j) {   // the first NS tiles were issued in the prologue
                 const int s = j % NS;
-                mbar_wait(&kv_empty[s], ((j / NS) & 1) ^ 1);
+                mbar_wait_backoff(&kv_empty[s], ((j / NS) & 1) ^ 1);
                 mbar_expect_tx(&k_full[s], AF_KVTILE);
                 tma_load_2d(smem + AF2_SMEM_K + s * AF_KVTILE, &tmKV, &k_full[s], (a.H + h) * HD, b * a.N + j * AF_BKV);
                 mbar_expect_tx(&v_full[s], AF_KVTILE);
@@ -376,8 +376,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 const int s = j % NS;
                 const int valid = min(AF_BKV, a.N - j * AF_BKV);
                 const int ncols = (valid + 15) & ~15;
-                mbar_wait(&k_full[s], (j / NS) & 1);
-                if (j > 0) mbar_wait(s_free, (j - 1) & 1);
+                mbar_wait_backoff(&k_full[s], (j / NS) & 1);
+                if (j > 0) mbar_wait_backoff(s_free, (j - 1) & 1);
                 tc_fence_after_sync();
                 const uint32_t idesc = make_idesc_bf16(128, ncols, 0, 0);
                 const uint64_t adesc = make_smem_desc_sw128(q_addr, 0, 1024);
@@ -387,7 +387,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 umma_commit(s_full);
             };
             VITK_TRACE_EV(a.trace, 1);
-            mbar_wait(q_full, 0);
+            mbar_wait_backoff(q_full, 0);
             issue_s(0);
             VITK_TRACE_EV(a.trace, 2);
             for (int j = 0; j < nkv; ++j) {
@@ -395,13 +395,13 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 if (j + 1 < nkv) issue_s(j + 1);
                 const int valid = min(AF_BKV, a.N - j * AF_BKV);
                 const int ksteps = (valid + 15) >> 4;
-                mbar_wait(&v_full[ks], (j / NS) & 1);
+                mbar_wait_backoff(&v_full[ks], (j / NS) & 1);
                 // O_g[128, HD] += P_j[128, 32g..32g+31] * V_j[32g..32g+31, HD]: A = P (K-major), B = V read MN-major
                 constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, 0, 1);
                 const uint32_t v_addr = smem_u32(smem + AF2_SMEM_V + ks * AF_KVTILE);
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
-                    mbar_wait(&p_full[2 * g + s], (j >> 1) & 1);
+                    mbar_wait_backoff(&p_full[2 * g + s], (j >> 1) & 1);
                     tc_fence_after_sync();
                     for (int k = 2 * g; k < ksteps && k < 2 * g + 2; ++k) {
                         const uint64_t adesc = make_smem_desc_sw128(p_addr + s * AF_QTILE + k * 32, 0, 1024);
