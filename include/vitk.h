@@ -151,6 +151,21 @@ int vitk_sgd_chunk_elems(void);
 int vitk_sgd_momentum_multi(const void* table, const void* chunk_map, int num_chunks, float lr, float momentum,
                             float grad_scale, int first_step, void* stream);
 
+/* Same update with the hyper-parameters read from DEVICE memory: hyper = { lr, momentum, grad_scale } (fp32). A step
+ * captured in a CUDA graph then follows the reference's LambdaLR schedule (utils_network.py:218-225) without
+ * re-capture: the host rewrites `hyper` (stream-ordered copy) between replays. */
+int vitk_sgd_momentum_multi_hp(const void* table, const void* chunk_map, int num_chunks, const float* hyper,
+                               void* stream);
+
+/* Multi-tensor Adam / AdamW (torch.optim.Adam / AdamW without amsgrad / maximize: the reference's 'adam' and 'adamw'
+ * optimisers, utils_network.py:119-126), fused with the bf16 weight refresh. table: device array of
+ * { float* p; const float* g; float* exp_avg; float* exp_avg_sq; bf16* w_or_null; int64 n } per tensor; chunk_map as
+ * for SGD. hyper (device, fp32[11], read AND written) = { lr, beta1, beta2, eps, weight_decay, decoupled (1 = AdamW,
+ * 0 = Adam: L2 term added to the gradient), 1-beta1, 1-beta2, step, step_size, inv_sqrt_bias2 }: each call first advances
+ * `step` by one and derives the last two (bias corrections) on the device, so the step counter is graph-capturable.
+ * Two launches. */
+int vitk_adam_multi(const void* table, const void* chunk_map, int num_chunks, float* hyper, void* stream);
+
 /* fp32 -> bf16 cast of n elements (weights, activations). n % 8 == 0 not required. */
 int vitk_cast_f32_bf16(const float* x, void* y_bf16, long long n, void* stream);
 

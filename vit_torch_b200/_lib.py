@@ -41,6 +41,8 @@ SIGNATURES = {
     "vitk_cast_f32_bf16": [_P, _P, _L, _P],
     "vitk_sgd_chunk_elems": [],
     "vitk_sgd_momentum_multi": [_P, _P, _I, _F, _F, _F, _I, _P],
+    "vitk_sgd_momentum_multi_hp": [_P, _P, _I, _P, _P],
+    "vitk_adam_multi": [_P, _P, _I, _P, _P],
     "vitk_attn_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "vitk_th_mix_fwd": [_P, _P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _P],
     "vitk_th_mix_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

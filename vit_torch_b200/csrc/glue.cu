@@ -409,7 +409,12 @@ constexpr int SGD_CHUNK = 16384;  // elements per thread block
 
 __global__ void __launch_bounds__(256)
 sgd_momentum_multi_kernel(const SgdTensor* __restrict__ tab, const int2* __restrict__ chunks, float lr, float momentum,
-                          float gscale, int first_step) {
+                          float gscale, int first_step, const float* __restrict__ hp) {
+    if (hp != nullptr) {   // hyper-parameters from device memory: a captured CUDA graph follows LambdaLR without re-capture
+        lr = hp[0];
+        momentum = hp[1];
+        gscale = hp[2];
+    }
     const int2 ck = chunks[blockIdx.x];  // x = tensor index, y = chunk index within the tensor
     const SgdTensor t = tab[ck.x];
     const long long base = (long long)ck.y * SGD_CHUNK;
@@ -443,6 +448,82 @@ sgd_momentum_multi_kernel(const SgdTensor* __restrict__ tab, const int2* __restr
             t.buf[i] = b; t.p[i] = p;
             if (t.w != nullptr) t.w[i] = __float2bfloat16_rn(p);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-tensor Adam / AdamW (torch.optim.Adam / AdamW semantics without amsgrad / maximize; the reference's 'adam' and
+// 'adamw' entries, utils_network.py:119-126) fused with the bf16 weight refresh, same table / chunk scheme as SGD.
+// All hyper-parameters AND the step counter live in device memory `hp` (so a captured CUDA graph advances the bias
+// corrections by itself): hp = { lr, beta1, beta2, eps, weight_decay, decoupled (1 = AdamW), 1-beta1, 1-beta2 (rounded
+// from double on the host, as torch does), step, step_size, inv_sqrt_bias2 }. adam_tick_kernel advances step and derives
+// the last two in double precision, once per launch.
+//   AdamW: p *= 1 - lr*wd           Adam: g += wd*p
+//   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= step_size * m / (sqrt(v) * inv_sqrt_bias2 + eps)
+// ------------------------------------------------------------------------------------------------
+struct AdamTensor {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    __nv_bfloat16* w;  // may be null
+    long long n;
+};
+
+__global__ void adam_tick_kernel(float* __restrict__ hp) {
+    const double step = (double)hp[8] + 1.0;
+    const double b1 = hp[1], b2 = hp[2];
+    const double bias1 = 1.0 - pow(b1, step), bias2 = 1.0 - pow(b2, step);
+    hp[8] = (float)step;
+    hp[9] = (float)((double)hp[0] / bias1);
+    hp[10] = (float)(1.0 / sqrt(bias2));
+}
+
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float lr, float b1, float b2,
+                                            float omb1, float omb2, float eps, float wd, bool decoupled,
+                                            float step_size, float isb2) {
+    if (wd != 0.f) {
+        if (decoupled) p *= 1.f - lr * wd;
+        else g = fmaf(wd, p, g);
+    }
+    m = fmaf(b1, m, omb1 * g);             // torch: exp_avg.lerp_(grad, 1 - beta1)
+    v = fmaf(b2, v, omb2 * g * g);
+    const float denom = fmaf(sqrtf(v), isb2, eps);
+    p -= step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const AdamTensor* __restrict__ tab, const int2* __restrict__ chunks, const float* __restrict__ hp) {
+    const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], omb1 = hp[6], omb2 = hp[7];
+    const float step_size = hp[9], isb2 = hp[10];
+    const bool decoupled = hp[5] != 0.f;
+    const int2 ck = chunks[blockIdx.x];
+    const AdamTensor t = tab[ck.x];
+    const long long base = (long long)ck.y * SGD_CHUNK;
+    const long long end = min(base + SGD_CHUNK, t.n);
+    const bool vec = ((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g) |
+                       reinterpret_cast<uintptr_t>(t.m) | reinterpret_cast<uintptr_t>(t.v)) & 15) == 0 &&
+                     (t.w == nullptr || (reinterpret_cast<uintptr_t>(t.w) & 7) == 0);
+    const long long end4 = vec ? base + ((end - base) & ~3LL) : base;
+    for (long long i = base + threadIdx.x * 4; i < end4; i += 256 * 4) {
+        const float4 g = *reinterpret_cast<const float4*>(t.g + i);
+        float4 p = *reinterpret_cast<const float4*>(t.p + i);
+        float4 m = *reinterpret_cast<const float4*>(t.m + i);
+        float4 v = *reinterpret_cast<const float4*>(t.v + i);
+        adam_update(p.x, g.x, m.x, v.x, lr, b1, b2, omb1, omb2, eps, wd, decoupled, step_size, isb2);
+        adam_update(p.y, g.y, m.y, v.y, lr, b1, b2, omb1, omb2, eps, wd, decoupled, step_size, isb2);
+        adam_update(p.z, g.z, m.z, v.z, lr, b1, b2, omb1, omb2, eps, wd, decoupled, step_size, isb2);
+        adam_update(p.w, g.w, m.w, v.w, lr, b1, b2, omb1, omb2, eps, wd, decoupled, step_size, isb2);
+        *reinterpret_cast<float4*>(t.m + i) = m;
+        *reinterpret_cast<float4*>(t.v + i) = v;
+        *reinterpret_cast<float4*>(t.p + i) = p;
+        if (t.w != nullptr) *reinterpret_cast<uint2*>(t.w + i) = make_uint2(pack_bf16(p.x, p.y), pack_bf16(p.z, p.w));
+    }
+    for (long long i = end4 + threadIdx.x; i < end; i += 256) {
+        float p = t.p[i], m = t.m[i], v = t.v[i];
+        adam_update(p, t.g[i], m, v, lr, b1, b2, omb1, omb2, eps, wd, decoupled, step_size, isb2);
+        t.m[i] = m; t.v[i] = v; t.p[i] = p;
+        if (t.w != nullptr) t.w[i] = __float2bfloat16_rn(p);
     }
 }
 
@@ -866,7 +947,28 @@ extern "C" int vitk_sgd_momentum_multi(const void* table, const void* chunk_map,
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     sgd_momentum_multi_kernel<<<num_chunks, 256, 0, st>>>(reinterpret_cast<const SgdTensor*>(table),
                                                           reinterpret_cast<const int2*>(chunk_map), lr, momentum,
-                                                          grad_scale, first_step);
+                                                          grad_scale, first_step, nullptr);
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
+extern "C" int vitk_sgd_momentum_multi_hp(const void* table, const void* chunk_map, int num_chunks, const float* hyper,
+                                          void* stream) {
+    if (num_chunks < 0 || !hyper || (num_chunks > 0 && (!table || !chunk_map))) return VITK_ERR_ARG;
+    if (num_chunks == 0) return VITK_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    sgd_momentum_multi_kernel<<<num_chunks, 256, 0, st>>>(reinterpret_cast<const SgdTensor*>(table),
+                                                          reinterpret_cast<const int2*>(chunk_map), 0.f, 0.f, 1.f, 0,
+                                                          hyper);
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
+extern "C" int vitk_adam_multi(const void* table, const void* chunk_map, int num_chunks, float* hyper, void* stream) {
+    if (num_chunks < 0 || !hyper || (num_chunks > 0 && (!table || !chunk_map))) return VITK_ERR_ARG;
+    if (num_chunks == 0) return VITK_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    adam_tick_kernel<<<1, 1, 0, st>>>(hyper);
+    adam_multi_kernel<<<num_chunks, 256, 0, st>>>(reinterpret_cast<const AdamTensor*>(table),
+                                                  reinterpret_cast<const int2*>(chunk_map), hyper);
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
 }
 

@@ -426,6 +426,26 @@ def sgd_momentum_multi(table, chunk_map, num_chunks, lr, momentum, grad_scale=1.
 sgd_momentum_multi = _timed(sgd_momentum_multi) if "_timed" in globals() else sgd_momentum_multi
 
 
+def sgd_momentum_multi_hp(table, chunk_map, num_chunks, hyper):
+    """As sgd_momentum_multi with (lr, momentum, grad_scale) read from the device tensor `hyper` (fp32 [3])."""
+    global launch_count
+    _need_cuda(table, chunk_map, hyper)
+    lib = _lib.load()
+    check(lib.vitk_sgd_momentum_multi_hp(ptr(table), ptr(chunk_map), num_chunks, ptr(hyper), _stream()),
+          "vitk_sgd_momentum_multi_hp")
+    launch_count += 1
+
+
+def adam_multi(table, chunk_map, num_chunks, hyper):
+    """Multi-tensor Adam / AdamW step; `hyper` fp32 [11] on the device holds the hyper-parameters and the step counter
+    (include/vitk.h). Two launches (tick + update)."""
+    global launch_count
+    _need_cuda(table, chunk_map, hyper)
+    lib = _lib.load()
+    check(lib.vitk_adam_multi(ptr(table), ptr(chunk_map), num_chunks, ptr(hyper), _stream()), "vitk_adam_multi")
+    launch_count += 2
+
+
 def set_sm_limit(n: int) -> None:
     """Size persistent-kernel grids for at most n SMs (0 = all). See vitk_set_sm_limit."""
     check(_lib.load().vitk_set_sm_limit(int(n)), "vitk_set_sm_limit")

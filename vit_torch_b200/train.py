@@ -16,40 +16,67 @@ def reset_parameters_like_zoo(m: nn.Module) -> None:
         m.reset_parameters()
 
 
-class FusedSGD(torch.optim.Optimizer):
-    """torch.optim.SGD(params, lr, momentum) -- the reference's 'sgd' entry (utils_network.py:119-126) -- as ONE
-    multi-tensor kernel per step that also refreshes the bf16 GEMM-operand copies of the weights
-    (vitk_sgd_momentum_multi). Same constructor keywords, `param_groups[i]['lr']` stays the knob LambdaLR turns
-    (utils_network.py:218-225), state_dict() keeps torch's `momentum_buffer` naming. dampening / nesterov /
-    weight_decay other than the reference's zeros raise."""
+class _FusedMultiTensor(torch.optim.Optimizer):
+    """Shared plumbing of the fused multi-tensor optimisers: ONE kernel per step over a device table of per-tensor
+    pointers (parameter, gradient, state buffers, live bf16 GEMM-operand copy), hyper-parameters in DEVICE memory so
+    that a step captured in a CUDA graph keeps following `param_groups[i]['lr']` (the knob the reference's LambdaLR
+    turns, utils_network.py:218-225): sync_hyper() rewrites them with a stream-ordered copy whenever they changed."""
 
-    def __init__(self, params, lr=1e-3, momentum=0.0, dampening=0, weight_decay=0, nesterov=False):
-        if dampening != 0 or weight_decay != 0 or nesterov:
-            raise NotImplementedError("FusedSGD implements the reference configuration: plain momentum SGD")
-        super().__init__(params, dict(lr=lr, momentum=momentum, dampening=0, weight_decay=0, nesterov=False))
+    _state_names: tuple = ()
+    _hp_sync_len = 0          # leading entries of the device hyper-parameter vector owned by the host
+    _hp_len = 0
+
+    def _init_fused(self):
         self._plan = {}       # group index -> cached launch plan
         self._pinned = []     # rotating pinned staging buffers for the pointer tables
         self._slot = 0
+        self._hp_dev = {}     # group index -> device fp32 vector
+        self._hp_host = {}    # group index -> last values written
+
+    def _hyper(self, group) -> list:
+        raise NotImplementedError
+
+    def _launch(self, plan, hp_dev) -> None:
+        raise NotImplementedError
+
+    def _hp(self, gi, dev):
+        if gi not in self._hp_dev:
+            self._hp_dev[gi] = torch.zeros((self._hp_len,), dtype=torch.float32, device=dev)
+            self._hp_host[gi] = None
+        return self._hp_dev[gi]
+
+    def sync_hyper(self) -> None:
+        """Make the device copies of the hyper-parameters match param_groups (no-op when nothing changed). Called by
+        step(); the graph Trainer calls it before every replay."""
+        for gi, group in enumerate(self.param_groups):
+            if gi not in self._hp_dev:
+                continue
+            cur = [float(v) for v in self._hyper(group)]
+            if cur != self._hp_host[gi]:
+                self._hp_dev[gi][: self._hp_sync_len].copy_(torch.tensor(cur, dtype=torch.float32), non_blocking=False)
+                self._hp_host[gi] = cur
 
     def _build_plan(self, ps, dev):
         import numpy as np
 
         from . import ops
         chunk = ops._lib.load().vitk_sgd_chunk_elems()
+        ncol = 4 + len(self._state_names)
         rows, cmap, ws = [], [], []
         for t, p in enumerate(ps):
             st = self.state[p]
-            if "momentum_buffer" not in st:  # torch: buf = g on the first step == momentum * 0 + g
-                st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            for nm in self._state_names:
+                if nm not in st:   # zeros reproduce torch's first step (buf = g; exp_avg = (1 - beta1) g; ...)
+                    st[nm] = torch.zeros_like(p, memory_format=torch.contiguous_format)
             w = self._bf16_copy(p)
             ws.append(w)
-            rows.append([p.data_ptr(), 0, st["momentum_buffer"].data_ptr(), w.data_ptr() if w is not None else 0,
-                         p.numel()])
+            rows.append([p.data_ptr(), 0] + [st[nm].data_ptr() for nm in self._state_names] +
+                        [w.data_ptr() if w is not None else 0, p.numel()])
             cmap += [(t, c) for c in range((p.numel() + chunk - 1) // chunk)]
-        table = np.asarray(rows, dtype=np.int64).reshape(-1, 5)
+        table = np.asarray(rows, dtype=np.int64).reshape(-1, ncol)
         cmap_dev = torch.tensor(cmap, dtype=torch.int32).view(-1, 2).to(dev)
         return dict(ids=[id(p) for p in ps], table=table, cmap=cmap_dev, nchunks=len(cmap), ws=ws,
-                    dev_table=torch.empty((len(ps), 5), dtype=torch.int64, device=dev))
+                    dev_table=torch.empty((len(ps), ncol), dtype=torch.int64, device=dev))
 
     @staticmethod
     def _bf16_copy(p):
@@ -70,7 +97,8 @@ class FusedSGD(torch.optim.Optimizer):
                 continue
             for p in ps:
                 if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
-                    raise ops._lib.VitkError("FusedSGD needs contiguous fp32 CUDA parameters (no CPU fallback)")
+                    raise ops._lib.VitkError(f"{type(self).__name__} needs contiguous fp32 CUDA parameters "
+                                             "(no CPU fallback)")
             plan = self._plan.get(gi)
             if (plan is None or plan["ids"] != [id(p) for p in ps]
                     or any(self._bf16_copy(p) is not w for p, w in zip(ps, plan["ws"]))):
@@ -83,17 +111,91 @@ class FusedSGD(torch.optim.Optimizer):
                 tab[t, 0] = p.data_ptr()
                 tab[t, 1] = g.data_ptr()
             if len(self._pinned) < 8:
-                self._pinned.append(torch.empty((len(ps), 5), dtype=torch.int64).pin_memory())
+                self._pinned.append(torch.empty(tab.shape, dtype=torch.int64).pin_memory())
             pin = self._pinned[self._slot % len(self._pinned)]
             self._slot += 1
-            if pin.shape != (len(ps), 5):
-                pin = self._pinned[(self._slot - 1) % len(self._pinned)] = torch.empty((len(ps), 5),
-                                                                                        dtype=torch.int64).pin_memory()
+            if pin.shape != tab.shape:
+                pin = self._pinned[(self._slot - 1) % len(self._pinned)] = torch.empty(tab.shape,
+                                                                                       dtype=torch.int64).pin_memory()
             pin.numpy()[...] = tab
             plan["dev_table"].copy_(pin, non_blocking=True)
-            ops.sgd_momentum_multi(plan["dev_table"], plan["cmap"], plan["nchunks"], group["lr"], group["momentum"],
-                                   1.0, False)
+            hp = self._hp(gi, ps[0].device)
+            if not torch.cuda.is_current_stream_capturing():
+                self.sync_hyper()     # (a capture records the launch only; the values are synced around it)
+            self._launch(plan, hp)
         return loss
+
+
+class FusedSGD(_FusedMultiTensor):
+    """torch.optim.SGD(params, lr, momentum) -- the reference's 'sgd' entry (utils_network.py:119-126) -- as ONE
+    multi-tensor kernel per step that also refreshes the bf16 GEMM-operand copies of the weights
+    (vitk_sgd_momentum_multi_hp). Same constructor keywords, `param_groups[i]['lr']` stays the knob LambdaLR turns
+    (utils_network.py:218-225), state_dict() keeps torch's `momentum_buffer` naming. dampening / nesterov /
+    weight_decay other than the reference's zeros raise."""
+
+    _state_names = ("momentum_buffer",)
+    _hp_sync_len = 3
+    _hp_len = 3
+
+    def __init__(self, params, lr=1e-3, momentum=0.0, dampening=0, weight_decay=0, nesterov=False):
+        if dampening != 0 or weight_decay != 0 or nesterov:
+            raise NotImplementedError("FusedSGD implements the reference configuration: plain momentum SGD")
+        super().__init__(params, dict(lr=lr, momentum=momentum, dampening=0, weight_decay=0, nesterov=False))
+        self._init_fused()
+
+    def _hyper(self, group):
+        return [group["lr"], group["momentum"], 1.0]
+
+    def _launch(self, plan, hp_dev):
+        from . import ops
+        ops.sgd_momentum_multi_hp(plan["dev_table"], plan["cmap"], plan["nchunks"], hp_dev)
+
+
+class FusedAdam(_FusedMultiTensor):
+    """torch.optim.Adam(params, lr, betas, eps, weight_decay) -- the reference's 'adam' entry
+    (utils_network.py:119-126) -- as one multi-tensor kernel (+ a one-thread tick kernel that advances the step counter
+    and the bias corrections on the device) that also refreshes the bf16 weight copies (vitk_adam_multi). State keeps
+    torch's names (`step`, `exp_avg`, `exp_avg_sq`; `step` is one device scalar shared by the group). amsgrad /
+    maximize raise."""
+
+    _state_names = ("exp_avg", "exp_avg_sq")
+    _hp_sync_len = 8
+    _hp_len = 11
+    _decoupled = False
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False, maximize=False):
+        if amsgrad or maximize:
+            raise NotImplementedError(f"{type(self).__name__}: amsgrad / maximize are not implemented")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False))
+        self._init_fused()
+
+    def _hyper(self, group):
+        b1, b2 = group["betas"]
+        return [group["lr"], b1, b2, group["eps"], group["weight_decay"], 1.0 if self._decoupled else 0.0,
+                1.0 - b1, 1.0 - b2]
+
+    def _build_plan(self, ps, dev):
+        plan = super()._build_plan(ps, dev)
+        gi = next(i for i, g in enumerate(self.param_groups) if any(p is ps[0] for p in g["params"]))
+        step = self._hp(gi, dev)[8]
+        for p in ps:
+            self.state[p]["step"] = step      # 0-d view of the group's device step counter
+        return plan
+
+    def _launch(self, plan, hp_dev):
+        from . import ops
+        ops.adam_multi(plan["dev_table"], plan["cmap"], plan["nchunks"], hp_dev)
+
+
+class FusedAdamW(FusedAdam):
+    """torch.optim.AdamW (decoupled weight decay, default 1e-2): the reference's 'adamw' entry."""
+
+    _decoupled = True
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=False,
+                 maximize=False):
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad,
+                         maximize=maximize)
 
 
 class Trainer:
@@ -103,11 +205,19 @@ class Trainer:
     ms/step -- and hung at process-group teardown; the arithmetic and launch sequence are those of the eager step)."""
 
     def __init__(self, model: nn.Module, lr: float = 1e-3, momentum: float = 0.9, reducer=None, fused_opt: bool = True,
-                 graph: bool = False):
+                 graph: bool = False, optimizer: str = "sgd"):
         self.model = model
         self.reducer = reducer
         params = [p for p in model.parameters() if p.requires_grad]
-        self.opt = (FusedSGD if fused_opt else torch.optim.SGD)(params, lr=lr, momentum=momentum)
+        # `optimizer`: the reference's --opt names (utils_network.py:119-126); sgd / adam / adamw have fused kernels
+        if optimizer == "sgd":
+            self.opt = (FusedSGD if fused_opt else torch.optim.SGD)(params, lr=lr, momentum=momentum)
+        elif optimizer == "adam":
+            self.opt = (FusedAdam if fused_opt else torch.optim.Adam)(params, lr=lr)
+        elif optimizer == "adamw":
+            self.opt = (FusedAdamW if fused_opt else torch.optim.AdamW)(params, lr=lr)
+        else:
+            raise NotImplementedError(f"optimizer {optimizer!r}: pass a torch.optim optimiser through the reference loop")
         self.extra_launches_per_step = 0
         self.use_graph = bool(graph) and reducer is None
         self._graph = None
@@ -149,6 +259,8 @@ class Trainer:
         return (self._sx, self._sy) if self._graph is not None else None
 
     def step_static(self) -> torch.Tensor:
+        if hasattr(self.opt, "sync_hyper"):
+            self.opt.sync_hyper()       # lr schedules act on the captured step through device-resident hyper-parameters
         self._graph.replay()
         return self._sloss
 
