@@ -35,6 +35,7 @@ struct AttnBwdArgs {
     float* dbias;               // optional fp32 [3D], += column sums of dqkv (gradient of the qkv Linear bias)
     long long* trace;           // instrumented build only (VITK_TRACE), else nullptr
     int dbg_skip;               // instrumented build only: 1 = skip the dQ kernel, 2 = skip the dK/dV kernel
+    int pf_dist;                // two-group kernels: CTA i pulls the tiles of CTA i + pf_dist into L2 (0 = off)
 };
 
 #ifdef VITK_TRACE
@@ -563,6 +564,24 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
                 tma_load_2d(smem + DQ2_SMEM_V + s * AB_T64, &tmQKV64, &kv_full[s], (2 * a.H + h) * HD, b * a.N + j * 64);
             }
         }
+        // L2 prefetch for the CTA that will run one wave later on this SM slot (see attn_fwd2_kernel)
+        if (lane == 1 && a.pf_dist > 0) {
+            const long long lin = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z) +
+                                  a.pf_dist;
+            if (lin < (long long)gridDim.x * gridDim.y * gridDim.z) {
+                const int pq = (int)(lin % gridDim.x), phb = (int)(lin / gridDim.x);
+                const int ph = phb % (int)gridDim.y, pb = phb / (int)gridDim.y;
+                tma_prefetch_l2_2d(&tmQKV128, ph * HD, pb * a.N + pq * 128);
+                tma_prefetch_l2_2d(&tmDO128, ph * HD, pb * a.N + pq * 128);
+                tma_prefetch_l2_2d(&tmO128, ph * HD, pb * a.N + pq * 128);
+                if (pq == 0) {
+                    for (int j = 0; j < nkv; ++j) {
+                        tma_prefetch_l2_2d(&tmQKV64, (a.H + ph) * HD, pb * a.N + j * 64);
+                        tma_prefetch_l2_2d(&tmQKV64, (2 * a.H + ph) * HD, pb * a.N + j * 64);
+                    }
+                }
+            }
+        }
     } else if (warp == 9) {
         if (lane == 0) {
             const uint32_t q_addr = smem_u32(smem + DQ2_SMEM_Q), do_addr = smem_u32(smem + DQ2_SMEM_DO);
@@ -808,6 +827,23 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
                 tma_load_2d(smem + DKV2_SMEM_DO + s * AB_T64, &tmDO64, &qdo_full[s], h * HD, b * a.N + i * 64);
             }
         }
+        // L2 prefetch for the CTA that will run one wave later on this SM slot (see attn_fwd2_kernel)
+        if (lane == 1 && a.pf_dist > 0) {
+            const long long lin = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z) +
+                                  a.pf_dist;
+            if (lin < (long long)gridDim.x * gridDim.y * gridDim.z) {
+                const int pk = (int)(lin % gridDim.x), phb = (int)(lin / gridDim.x);
+                const int ph = phb % (int)gridDim.y, pb = phb / (int)gridDim.y;
+                tma_prefetch_l2_2d(&tmQKV128, (a.H + ph) * HD, pb * a.N + pk * 128);
+                tma_prefetch_l2_2d(&tmQKV128, (2 * a.H + ph) * HD, pb * a.N + pk * 128);
+                if (pk == 0) {
+                    for (int i = 0; i < nq; ++i) {
+                        tma_prefetch_l2_2d(&tmQKV64, ph * HD, pb * a.N + i * 64);
+                        tma_prefetch_l2_2d(&tmDO64, ph * HD, pb * a.N + i * 64);
+                    }
+                }
+            }
+        }
     } else if (warp == 9) {
         if (lane == 0) {
             const uint32_t k_addr = smem_u32(smem + DKV2_SMEM_K), v_addr = smem_u32(smem + DKV2_SMEM_V);
@@ -987,6 +1023,7 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
 
 int make_tok_tmap2d(CUtensorMap* out, const void* p, long long rows, long long cols, int box_rows);  // attn_fwd.cu
 bool attn_two_groups();  // attn_fwd.cu (VITK_ATTN_WG2)
+int attn_prefetch_dist();  // attn_fwd.cu (VITK_ATTN_PREFETCH)
 
 template <int HD>
 static int launch_attn_bwd(const CUtensorMap& q128, const CUtensorMap& q64, const CUtensorMap& do128,
@@ -1044,6 +1081,7 @@ static int attn_bwd_impl(const void* qkv_bf16, const void* out_bf16, const void*
     a.dbias = dbias;
     a.trace = nullptr;
     a.dbg_skip = 0;
+    a.pf_dist = attn_prefetch_dist();
 #ifdef VITK_TRACE
     a.trace = g_attn_trace;
     if (const char* e = getenv("VITK_ATTN_DBG_SKIP")) a.dbg_skip = atoi(e);
