@@ -18,7 +18,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, overlap, ret):
+def _worker(rank, world, port, overlap, ret, arena=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -36,6 +36,12 @@ def _worker(rank, world, port, overlap, ret):
     # emulate one block bucket: layer 0's grads live in a flat buffer whose views are the .grad tensors
     p0 = list(model[0].parameters())
     flat = torch.cat([p.grad.reshape(-1) for p in p0])
+    if arena:   # the Trainer's gradient arena: bucket buffers are adjacent slices of one buffer -> one collective
+        Fn.grad_arena = Fn.GradArena(1024, torch.device("cpu"))
+        Fn.grad_arena.begin()
+        a = Fn.grad_arena.take(flat.numel(), flat.device)
+        a.copy_(flat)
+        flat = a
     views, off = [], 0
     for p in p0:
         v = flat[off:off + p.numel()].view(p.shape)
@@ -45,17 +51,20 @@ def _worker(rank, world, port, overlap, ret):
     for hook in Fn.grad_bucket_hooks:
         hook(flat, p0, views)
     red.finish()
+    if arena:
+        assert red.collectives == 2     # one over the arena, one for the parameters outside any bucket
+        Fn.grad_arena = None
     ret[rank] = [p.grad.clone() for p in model.parameters()]
     red.close()
     assert len(Fn.grad_bucket_hooks) == 0
     dist.destroy_process_group()
 
 
-def _run(overlap):
+def _run(overlap, arena=False):
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), overlap, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), overlap, ret, arena), nprocs=world, join=True)
     # reference: average of the per-rank gradients computed in this process
     torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.Linear(8, 4))
@@ -79,3 +88,7 @@ def test_grad_allreduce_overlapped_gloo():
 
 def test_grad_allreduce_deferred_gloo():
     _run(False)
+
+
+def test_grad_allreduce_deferred_arena_gloo():
+    _run(False, arena=True)

@@ -16,6 +16,9 @@ import torch.distributed as dist
 from . import functional as Fn
 
 
+_partition_limit = 0     # SMs left to the persistent kernels while collectives overlap them (0 = no partition)
+
+
 def configure_sm_partition(nccl_ctas: int = 4) -> None:
     """Call BEFORE dist.init_process_group. Caps the NCCL kernels at `nccl_ctas` thread blocks (NCCL_MAX_CTAS, unless
     the user already set it) and sizes the persistent GEMM grids for the remaining SMs. The GEMMs are statically
@@ -28,9 +31,14 @@ def configure_sm_partition(nccl_ctas: int = 4) -> None:
     from . import ops
     if nccl_ctas <= 0:
         return
+    global _partition_limit
     os.environ.setdefault("NCCL_MAX_CTAS", str(nccl_ctas))
     n = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
-    ops.set_sm_limit(max(n - int(os.environ["NCCL_MAX_CTAS"]), n // 2))
+    # The limit is applied only while all-reduces are in flight (GradAllReducer: from the first bucket of a backward
+    # pass until finish()): forward, loss and optimiser run on all SMs. ViT-B/16 bs128 has 591 output tiles in its
+    # N = 768 GEMMs -- 3.99 waves on 148 SMs but 4.10 (= 5 rounds) on 144 -- so a permanent limit costs the forward
+    # proj / fc2 GEMMs a whole extra round.
+    _partition_limit = max(n - int(os.environ["NCCL_MAX_CTAS"]), n // 2)
 
 
 class GradAllReducer:
@@ -44,6 +52,7 @@ class GradAllReducer:
         self._pending = []   # (flat buffer, work handle)
         self._bucketed_ptrs = set()
         self.collectives = 0
+        self._limited = False
         if self.world > 1:
             Fn.grad_bucket_hooks.append(self._on_bucket)
 
@@ -57,6 +66,10 @@ class GradAllReducer:
             self._pending.append((buf, None, params, views))
             return
         if self.cuda:
+            if _partition_limit and not self._limited:      # collectives in flight from here to finish()
+                from . import ops
+                ops.set_sm_limit(_partition_limit)
+                self._limited = True
             ev = torch.cuda.Event()
             ev.record()
             with torch.cuda.stream(self.comm_stream):
@@ -73,14 +86,32 @@ class GradAllReducer:
         param.grad holds the averaged gradient. Call after loss.backward(), before optimizer.step()."""
         if self.world <= 1:
             return
+        if self._limited:       # what is launched from here on is ordered after the joined collectives: all SMs again
+            from . import ops
+            ops.set_sm_limit(0)
+            self._limited = False
         covered = set()
+        # deferred mode with a gradient arena (train.Trainer): the blocks' buffers are adjacent slices of one buffer,
+        # so ONE collective at full NVLink bandwidth covers them all
+        coalesced = False
+        arena = Fn.grad_arena
+        if (arena is not None and self._pending and all(w is None for _, w, _, _ in self._pending)
+                and all(b.untyped_storage().data_ptr() == arena.buf.untyped_storage().data_ptr()
+                        for b, _, _, _ in self._pending)):
+            dist.all_reduce(arena.used(), op=dist.ReduceOp.AVG if self.cuda else dist.ReduceOp.SUM, group=self.pg)
+            self.collectives += 1
+            if not self.cuda:
+                arena.used().div_(self.world)
+            coalesced = True
         for buf, work, params, views in self._pending:
-            if work is None:
+            if coalesced:
+                pass
+            elif work is None:
                 dist.all_reduce(buf, op=dist.ReduceOp.AVG if self.cuda else dist.ReduceOp.SUM, group=self.pg)
                 self.collectives += 1
             else:
                 work.wait()
-            if not self.cuda:
+            if not self.cuda and not coalesced:
                 buf.div_(self.world)
             # .grad normally IS the bucket view (autograd steals it when .grad was None); if autograd cloned or
             # accumulated instead, overwrite it with the reduced bucket contents.

@@ -39,11 +39,44 @@ def bf16_weight(p: torch.Tensor) -> torch.Tensor:
     return w
 
 
+class GradArena:
+    """One persistent fp32 buffer that the per-block flat gradient buffers of a step are carved from (opt-in: the
+    Trainer owns one). begin() zeroes it with a single memset -- instead of one torch fill per block -- and rewinds it;
+    because the blocks' buffers are then adjacent, a data-parallel step can all-reduce them with ONE collective
+    (dist.GradAllReducer, deferred mode). Gradients handed out are views: they are valid until the next begin()."""
+
+    def __init__(self, numel: int, device):
+        self.buf = torch.zeros((max(int(numel), 4),), dtype=torch.float32, device=device)
+        self.off = 0
+        self.high = 0            # high-water mark of the last step: only that part needs zeroing / reducing
+
+    def begin(self) -> None:
+        self.high = max(self.high, self.off)
+        if self.high:
+            self.buf[: self.high].zero_()
+        self.off = 0
+
+    def take(self, n: int, device):
+        if self.buf.device != device or self.off + n > self.buf.numel():
+            return None
+        out = self.buf[self.off:self.off + n]
+        self.off += n
+        return out
+
+    def used(self) -> torch.Tensor:
+        return self.buf[: self.off]
+
+
+grad_arena: GradArena | None = None      # set by train.Trainer; None = every block allocates its own zero buffer
+
+
 def _flat_grads(params, needs, device):
     """One contiguous fp32 zero buffer holding the gradients of all params that need one; returns views."""
     sizes = [p.numel() if (p is not None and need) else 0 for p, need in zip(params, needs)]
     total = sum(((s + 3) // 4) * 4 for s in sizes)  # keep every view 16-byte aligned
-    buf = torch.zeros((max(total, 4),), dtype=torch.float32, device=device)
+    buf = grad_arena.take(max(total, 4), device) if grad_arena is not None else None
+    if buf is None:
+        buf = torch.zeros((max(total, 4),), dtype=torch.float32, device=device)
     views, off = [], 0
     for p, s in zip(params, sizes):
         if s == 0:

@@ -219,6 +219,12 @@ class Trainer:
         else:
             raise NotImplementedError(f"optimizer {optimizer!r}: pass a torch.optim optimiser through the reference loop")
         self.extra_launches_per_step = 0
+        # gradient arena: the per-block flat gradient buffers of a step are adjacent slices of one buffer (one memset
+        # per step; one all-reduce per step in deferred data-parallel mode)
+        self.arena = None
+        if params and params[0].is_cuda:
+            from . import functional
+            self.arena = functional.GradArena(sum((p.numel() + 3) // 4 * 4 + 4 for p in params), params[0].device)
         self.use_graph = bool(graph) and reducer is None
         self._graph = None
         self._sx = self._sy = self._sloss = None
@@ -227,6 +233,10 @@ class Trainer:
         self.last_correct = None        # 0-d device tensor: correct argmax predictions of the last step's batch
 
     def _step_eager(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if self.arena is not None:
+            from . import functional
+            functional.grad_arena = self.arena
+            self.arena.begin()              # (the previous step's gradients were consumed by its optimiser step)
         out = self.model(x)
         if out.dim() == 2 and out.dtype == torch.float32 and out.stride(1) == 1 and y.dtype == torch.int64:
             # fused loss + gradient + argmax-accuracy count (utils_network.py:85-95, 429-433), no host sync
