@@ -253,7 +253,7 @@ def main():
         for p in model.parameters():
             dist.broadcast(p.data, 0)
     trainer = train.Trainer(model, lr=1e-3, momentum=0.9, reducer=GradAllReducer(model, overlap=args.overlap)
-                            if world > 1 else None, graph=(world == 1 and not args.no_graph))
+                            if world > 1 else None, graph=(not args.no_graph))
 
     x_dev, y_dev = synth_batch(bs, size, 1000 + rank, dev)
     x_host = torch.empty((bs, 3, size, size), dtype=torch.float32).pin_memory()
@@ -411,7 +411,10 @@ def main():
                        "batch_per_gpu": bs, "global_batch": bs * world, "tokens": N, "parallelism": f"dp{world}",
                        "l2": "working set per step (>8 GB of activations) far exceeds the 126 MB L2; no explicit flush",
                        "numerics": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream + master weights",
-                       "launch": "whole step captured in one CUDA graph" if trainer.use_graph else "eager launches",
+                       "launch": ("eager launches" if not trainer.use_graph else
+                                  "whole step captured in one CUDA graph" if trainer.opt_in_graph else
+                                  "forward + loss + backward captured in one CUDA graph; all-reduce and optimiser "
+                                  "kernel launched after each replay"),
                        "grad_allreduce": ("none (1 GPU)" if world == 1 else
                                           f"per-block NCCL all-reduces overlapped with backward, NCCL_MAX_CTAS={args.nccl_ctas}"
                                           if args.overlap else

@@ -84,3 +84,28 @@ def test_graph_step_matches_eager_step():
             assert tr.static_inputs() is not None and tr.launches_per_step > 100
     for a, b in zip(losses[False], losses[True]):
         assert abs(a - b) <= 2e-3 * max(1.0, abs(a)), (losses[False], losses[True])
+
+
+def test_graph_step_with_eager_reduce_and_optimiser_tail():
+    """Data-parallel layout of the captured step (deferred all-reduce): forward + loss + backward replayed from a graph,
+    gradient reduction and the optimiser kernel launched after every replay. Single process (world 1: the collective is
+    a no-op), same losses as eager launches, also across an eager step with another batch size in between."""
+    import torch
+    from vit_torch_b200 import models, train
+    from vit_torch_b200.dist import GradAllReducer
+    torch.manual_seed(0)
+    sizes = [4, 4, 4, 4, 2, 4, 4]
+    xs = [torch.randn(b, 3, 224, 224, device="cuda") for b in sizes]
+    ys = [torch.randint(0, 10, (b,), device="cuda") for b in sizes]
+    losses = {}
+    for mode in (False, True):
+        torch.manual_seed(1)
+        m = models.dino_vits16(pretrained=False).cuda()
+        train.reset_parameters_like_zoo(m)
+        red = GradAllReducer(m, overlap=False)
+        tr = train.Trainer(m, lr=1e-2, graph=mode, reducer=red)
+        assert tr.use_graph == mode and not tr.opt_in_graph
+        losses[mode] = [tr.step(x, y).item() for x, y in zip(xs, ys)]
+        red.close()
+    for a, b in zip(losses[False], losses[True]):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(a)), (losses[False], losses[True])

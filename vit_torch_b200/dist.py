@@ -81,6 +81,37 @@ class GradAllReducer:
         self.collectives += 1
         self._pending.append((buf, work, params, views))
 
+    def discard_pending(self):
+        """Forget bucket notifications (used after a CUDA-graph capture of backward: replays fire no hooks)."""
+        self._pending.clear()
+
+    def finish_static(self, arena):
+        """Deferred reduction without bucket notifications (the Trainer replays a captured forward + backward): one
+        collective over the used part of the gradient arena, one over the gradients that live outside it."""
+        if self.world <= 1:
+            return
+        op = dist.ReduceOp.AVG if self.cuda else dist.ReduceOp.SUM
+        base = None
+        if arena is not None and arena.off > 0:
+            dist.all_reduce(arena.used(), op=op, group=self.pg)
+            if not self.cuda:
+                arena.used().div_(self.world)
+            self.collectives += 1
+            base = arena.buf.untyped_storage().data_ptr()
+        rest = [p.grad for p in self.model.parameters()
+                if p.grad is not None and (base is None or p.grad.untyped_storage().data_ptr() != base)]
+        if rest:
+            flat = torch.cat([g.reshape(-1) for g in rest])
+            dist.all_reduce(flat, op=op, group=self.pg)
+            if not self.cuda:
+                flat.div_(self.world)
+            self.collectives += 1
+            off = 0
+            for g in rest:
+                n = g.numel()
+                g.copy_(flat[off:off + n].view_as(g))
+                off += n
+
     def finish(self):
         """Join the overlapped collectives, reduce whatever was not covered by a block bucket, and make sure every
         param.grad holds the averaged gradient. Call after loss.backward(), before optimizer.step()."""

@@ -225,7 +225,11 @@ class Trainer:
         if params and params[0].is_cuda:
             from . import functional
             self.arena = functional.GradArena(sum((p.numel() + 3) // 4 * 4 + 4 for p in params), params[0].device)
-        self.use_graph = bool(graph) and reducer is None
+        # Data parallel: with the deferred all-reduce (dist.GradAllReducer(overlap=False)) forward + loss + backward are
+        # captured and the collective and the optimiser kernel run eagerly after the replay; the overlapped mode issues
+        # NCCL calls from inside backward and stays eager.
+        self.use_graph = bool(graph) and (reducer is None or not getattr(reducer, "overlap", True))
+        self.opt_in_graph = reducer is None
         self._graph = None
         self._sx = self._sy = self._sloss = None
         self._eager_steps = 0
@@ -233,6 +237,13 @@ class Trainer:
         self.last_correct = None        # 0-d device tensor: correct argmax predictions of the last step's batch
 
     def _step_eager(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        loss = self._fwd_bwd(x, y)
+        if self.reducer is not None:
+            self.reducer.finish()
+        self.opt.step()
+        return loss
+
+    def _fwd_bwd(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         if self.arena is not None:
             from . import functional
             functional.grad_arena = self.arena
@@ -247,9 +258,6 @@ class Trainer:
             self.last_correct = None
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
-        if self.reducer is not None:
-            self.reducer.finish()
-        self.opt.step()
         return loss.detach()
 
     def _capture(self, x: torch.Tensor, y: torch.Tensor) -> None:
@@ -260,18 +268,36 @@ class Trainer:
         self._graph = torch.cuda.CUDAGraph()
         n0 = ops.launch_count
         with torch.cuda.graph(self._graph):
-            self._sloss = self._step_eager(self._sx, self._sy)
+            if self.opt_in_graph:
+                self._sloss = self._step_eager(self._sx, self._sy)
+            else:
+                self._sloss = self._fwd_bwd(self._sx, self._sy)
         self.launches_per_step = ops.launch_count - n0
+        if not self.opt_in_graph:
+            self.reducer.discard_pending()      # bucket hooks fired during capture; replays reduce the arena directly
+            self.launches_per_step += 1         # the optimiser kernel launched after every replay
+            # the gradient tensors the captured backward writes: re-attached before every eager tail, because an eager
+            # step in between (another batch shape) replaces .grad
+            self._static_grads = [(p, p.grad) for p in self.model.parameters() if p.grad is not None]
 
     def static_inputs(self):
         """(images, labels) device buffers the captured step reads; fill them (e.g. `copy_` from pinned host memory)
         and call step_static(). None before the graph exists."""
         return (self._sx, self._sy) if self._graph is not None else None
 
+    def _finish_static(self) -> None:
+        """Data-parallel tail of a captured step: all-reduce the gradients (arena + the rest), then the optimiser."""
+        for p, g in self._static_grads:
+            p.grad = g
+        self.reducer.finish_static(self.arena)
+        self.opt.step()
+
     def step_static(self) -> torch.Tensor:
-        if hasattr(self.opt, "sync_hyper"):
+        if self.opt_in_graph and hasattr(self.opt, "sync_hyper"):
             self.opt.sync_hyper()       # lr schedules act on the captured step through device-resident hyper-parameters
         self._graph.replay()
+        if not self.opt_in_graph:
+            self._finish_static()
         return self._sloss
 
     def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
