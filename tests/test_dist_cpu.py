@@ -18,7 +18,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, overlap, ret, arena=False):
+def _worker(rank, world, port, overlap, ret, arena=False, static=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -48,9 +48,12 @@ def _worker(rank, world, port, overlap, ret, arena=False):
         p.grad = v                      # what autograd does when it adopts the returned view
         views.append(v.view(v.shape))   # alias handed to the hook
         off += p.numel()
-    for hook in Fn.grad_bucket_hooks:
-        hook(flat, p0, views)
-    red.finish()
+    if static:   # the graph Trainer's tail: no bucket notifications, the arena and the rest are reduced directly
+        red.finish_static(Fn.grad_arena)
+    else:
+        for hook in Fn.grad_bucket_hooks:
+            hook(flat, p0, views)
+        red.finish()
     if arena:
         assert red.collectives == 2     # one over the arena, one for the parameters outside any bucket
         Fn.grad_arena = None
@@ -60,11 +63,11 @@ def _worker(rank, world, port, overlap, ret, arena=False):
     dist.destroy_process_group()
 
 
-def _run(overlap, arena=False):
+def _run(overlap, arena=False, static=False):
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), overlap, ret, arena), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), overlap, ret, arena, static), nprocs=world, join=True)
     # reference: average of the per-rank gradients computed in this process
     torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.Linear(8, 4))
@@ -92,3 +95,7 @@ def test_grad_allreduce_deferred_gloo():
 
 def test_grad_allreduce_deferred_arena_gloo():
     _run(False, arena=True)
+
+
+def test_grad_allreduce_static_arena_gloo():
+    _run(False, arena=True, static=True)
