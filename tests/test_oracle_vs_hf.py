@@ -10,21 +10,24 @@ import torch
 transformers = pytest.importorskip("transformers")
 
 
-def _hf_from_oracle(ref, D, L, H, P):
-    from transformers import ViTConfig, ViTModel
-    cfg = ViTConfig(hidden_size=D, num_hidden_layers=L, num_attention_heads=H, intermediate_size=4 * D,
+def _hf_from_oracle(ref, D, L, H, P, distilled=False):
+    from transformers import DeiTConfig, DeiTModel, ViTConfig, ViTModel
+    Config, Model = (DeiTConfig, DeiTModel) if distilled else (ViTConfig, ViTModel)
+    cfg = Config(hidden_size=D, num_hidden_layers=L, num_attention_heads=H, intermediate_size=4 * D,
                     hidden_act="gelu", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, layer_norm_eps=1e-6,
                     image_size=224, patch_size=P, num_channels=3, qkv_bias=True)
     try:
         cfg._attn_implementation = "eager"
     except Exception:
         pass
-    hf = ViTModel(cfg, add_pooling_layer=False)
+    hf = Model(cfg, add_pooling_layer=False)
     sd = ref.state_dict()
     m = {"embeddings.cls_token": sd["cls_token"], "embeddings.position_embeddings": sd["pos_embed"],
          "embeddings.patch_embeddings.projection.weight": sd["patch_embed.proj.weight"],
          "embeddings.patch_embeddings.projection.bias": sd["patch_embed.proj.bias"],
          "layernorm.weight": sd["norm.weight"], "layernorm.bias": sd["norm.bias"]}
+    if distilled:
+        m["embeddings.distillation_token"] = sd["dist_token"]
     for i in range(L):
         b, h = f"blocks.{i}.", f"encoder.layer.{i}."
         qw, kw, vw = sd[b + "attn.qkv.weight"].chunk(3, 0)
@@ -74,3 +77,23 @@ def test_dino_vits16_restatement_matches_hf_vit():
     for a, b in pairs:
         e = ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
         assert e <= 1e-4, e
+
+
+def test_deit_distilled_restatement_matches_hf_deit():
+    """timm-style VisionTransformer with a distillation token (models/deit.py:20-59: N = n + 2, features = the normed cls
+    and dist rows) against HuggingFace DeiTModel."""
+    from oracle import vit as ovit
+    torch.manual_seed(0)
+    ref = ovit.TimmVisionTransformer(embed_dim=192, depth=3, num_heads=3, num_classes=0, distilled=True)
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        for n, p in ref.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.05 * torch.randn(p.shape, generator=g))
+    hf = _hf_from_oracle(ref, 192, 3, 3, 16, distilled=True)
+    x = torch.randn(2, 3, 224, 224, generator=g)
+    cls_ref, dist_ref = ref.forward_features(x)
+    h = hf(pixel_values=x).last_hidden_state
+    for a, b in ((cls_ref, h[:, 0]), (dist_ref, h[:, 1])):
+        err = ((a - b).abs().max() / b.abs().max()).item()
+        assert err <= 1e-5, err
