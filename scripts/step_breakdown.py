@@ -6,8 +6,12 @@ from vit_torch_b200 import models, train, ops
 name = sys.argv[1] if len(sys.argv) > 1 else "dino_vitb16"
 bs = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 torch.manual_seed(0)
-m = getattr(models, name)(pretrained=False).cuda()
-train.reset_parameters_like_zoo(m)
+if name.startswith("cait"):
+    from vit_torch_b200 import cait
+    m = getattr(cait, name)(pretrained=False, num_classes=10).cuda()
+else:
+    m = getattr(models, name)(pretrained=False).cuda()
+    train.reset_parameters_like_zoo(m)
 tr = train.Trainer(m)
 x = torch.randn(bs, 3, 224, 224, device="cuda"); y = torch.randint(0, 10, (bs,), device="cuda")
 for _ in range(3): tr.step(x, y)
