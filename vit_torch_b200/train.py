@@ -307,7 +307,16 @@ class Trainer:
             if self._eager_steps < 2:        # first steps eager: bf16 weight cache, optimiser state, autotuned plans
                 self._eager_steps += 1
                 return self._step_eager(x, y)
-            self._capture(x, y)
+            try:
+                self._capture(x, y)
+            except Exception as exc:    # keep training: fall back to eager launches (same kernels, same collectives)
+                import sys
+                print(f"[vit_torch_b200] CUDA-graph capture of the step failed ({type(exc).__name__}: {exc}); "
+                      "continuing with eager launches", file=sys.stderr)
+                self.use_graph = False
+                self._graph = None
+                torch.cuda.synchronize()
+                return self._step_eager(x, y)
         if x.shape != self._sx.shape or y.shape != self._sy.shape or x.dtype != self._sx.dtype:
             return self._step_eager(x, y)    # a different batch shape (e.g. the last batch of an epoch)
         if x.data_ptr() != self._sx.data_ptr():
