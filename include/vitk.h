@@ -110,7 +110,9 @@ int vitk_layernorm_bwd_ex(const void* dy, int dy_is_f32, const float* x, long lo
 
 /* Fused mean softmax cross-entropy + its gradient + argmax accuracy of logits fp32 [rows, C] (row pitch ld), labels
  * int64 [rows]: out2[0] = mean loss, out2[1] = number of rows whose first-maximum column equals the label (as a float),
- * dlogits (optional, row pitch ldd) = (softmax - onehot) / rows. Deterministic, no host synchronisation. Replaces
+ * dlogits (optional, row pitch ldd) = (softmax - onehot) / rows_that_count. Rows labelled -100 (nn.CrossEntropyLoss's
+ * default ignore_index) are left out of the mean and get a zero gradient; any other label outside [0, C) makes the loss
+ * NaN (torch raises a device assert there). Deterministic, no host synchronisation. Replaces
  * nn.CrossEntropyLoss + autograd (utils_network.py:429-433, main.py:244) and classification_count_correct
  * (utils_network.py:85-95). */
 int vitk_cross_entropy(const float* logits, long long ld, const long long* labels, int rows, int C, float* out2,
@@ -122,6 +124,10 @@ int vitk_colsum_f32(const float* x, long long ldx, long long rows, long long col
 /* out[c] += sum_r a_f32[r,c] * b_bf16[r,c]  (LayerScale d_gamma = sum_rows dY o f; models/cait.py:144-149). */
 int vitk_colsum_prod(const float* a, long long lda, const void* b_bf16, long long ldb, long long rows, int N, float* out,
                      void* stream);
+/* Same with the DropPath factor of the branch (models/cait.py:67,140,148-149; timm Block): the forward value is
+ * x + gamma * rowscale[row / rows_per_sample] * f, so d_gamma = sum_rows dY * rowscale * f. rowscale may be null. */
+int vitk_colsum_prod_ex(const float* a, long long lda, const void* b_bf16, long long ldb, long long rows, int N,
+                        float* out, const float* rowscale, long long rows_per_sample, void* stream);
 
 /* out_bf16[r,:] = bf16(x[(r / rows_per_group) * group_stride + (r % rows_per_group) * D + :] * colscale * rowscale[r / rows_per_sample])
  * -- the bf16 copy of a residual-stream gradient that the dgrad/wgrad GEMMs read (LayerScale / DropPath folded in),

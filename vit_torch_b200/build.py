@@ -56,9 +56,12 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    hdrs = _headers()
+    # the library travels to the GPU box without its object files: up to date = newer than every source and header
+    if not force and not _stale(LIB, sources() + hdrs):
+        return LIB
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
-    hdrs = _headers()
     jobs = []
     objs = []
     for src in sources():

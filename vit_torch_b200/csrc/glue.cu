@@ -553,7 +553,7 @@ colsum_f32_kernel(const float* __restrict__ x, long long ldx, long long rows, lo
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 colsum_prod_kernel(const float* __restrict__ a, long long lda, const __nv_bfloat16* __restrict__ b, long long ldb,
-                   long long rows, int N, float* __restrict__ out) {
+                   long long rows, int N, float* __restrict__ out, const float* __restrict__ rowscale, long long rps) {
     __shared__ float red[8][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int col = blockIdx.x * 256 + lane * 8;
@@ -561,8 +561,13 @@ colsum_prod_kernel(const float* __restrict__ a, long long lda, const __nv_bfloat
     if (col + 8 <= N) {
         for (long long r = (long long)blockIdx.y * 8 + warp; r < rows; r += (long long)gridDim.y * 8) {
             const uint4 v = ld_nc_v4(b + r * ldb + col);
-            const float4 a0 = *reinterpret_cast<const float4*>(a + r * lda + col);
-            const float4 a1 = *reinterpret_cast<const float4*>(a + r * lda + col + 4);
+            float4 a0 = *reinterpret_cast<const float4*>(a + r * lda + col);
+            float4 a1 = *reinterpret_cast<const float4*>(a + r * lda + col + 4);
+            if (rowscale != nullptr) {      // DropPath: the branch was scaled by mask / keep_prob per sample
+                const float rs = __ldg(rowscale + r / rps);
+                a0.x *= rs; a0.y *= rs; a0.z *= rs; a0.w *= rs;
+                a1.x *= rs; a1.y *= rs; a1.z *= rs; a1.w *= rs;
+            }
             acc[0] += a0.x * bf16_lo(v.x); acc[1] += a0.y * bf16_hi(v.x); acc[2] += a0.z * bf16_lo(v.y);
             acc[3] += a0.w * bf16_hi(v.y); acc[4] += a1.x * bf16_lo(v.z); acc[5] += a1.y * bf16_hi(v.z);
             acc[6] += a1.z * bf16_lo(v.w); acc[7] += a1.w * bf16_hi(v.w);
@@ -673,13 +678,33 @@ cross_entropy_kernel(const float* __restrict__ logits, long long ld, const long 
                      int C, float* __restrict__ out, float* __restrict__ dlogits, long long ldd) {
     __shared__ float s_loss[32];
     __shared__ int s_correct[32];
+    __shared__ int s_valid[32];
+    __shared__ int s_bad[32];
+    constexpr long long kIgnore = -100;   // nn.CrossEntropyLoss default ignore_index: such rows leave the mean
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const float inv_rows = 1.0f / (float)rows;
+    // pass 0: rows that count (torch divides by the number of non-ignored targets); any other out-of-range label is an
+    // error (torch device-asserts): the loss becomes NaN so that it cannot pass unnoticed
+    int nvalid = 0, nbad = 0;
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+        const long long l = labels[r];
+        if (l == kIgnore) continue;
+        if (l < 0 || l >= C) ++nbad;
+        ++nvalid;
+    }
+    nvalid = warp_sum(nvalid);
+    nbad = warp_sum(nbad);
+    if (lane == 0) { s_valid[warp] = nvalid; s_bad[warp] = nbad; }
+    __syncthreads();
+    nvalid = 0; nbad = 0;
+    for (int w = 0; w < nwarps; ++w) { nvalid += s_valid[w]; nbad += s_bad[w]; }
+    const float inv_rows = 1.0f / (float)nvalid;     // 0 valid rows: inf * 0 = NaN, as torch
     float loss = 0.f;
     int correct = 0;
     for (int r = warp; r < rows; r += nwarps) {
         const float* x = logits + (long long)r * ld;
-        const int label = (int)labels[r];
+        const long long label64 = labels[r];
+        const bool ignored = label64 == kIgnore;
+        const int label = (int)label64;
         float mx = -INFINITY;
         int arg = 0x7fffffff;
         for (int c = lane; c < C; c += 32) {
@@ -700,10 +725,10 @@ cross_entropy_kernel(const float* __restrict__ logits, long long ld, const long 
         if (dlogits != nullptr) {
             float* d = dlogits + (long long)r * ldd;
             for (int c = lane; c < C; c += 32)
-                d[c] = (__expf(x[c] - mx) * inv - (c == label ? 1.0f : 0.0f)) * inv_rows;
+                d[c] = ignored ? 0.f : (__expf(x[c] - mx) * inv - (c == label ? 1.0f : 0.0f)) * inv_rows;
         }
         if (lane == 0) {
-            loss += lse - ((label >= 0 && label < C) ? x[label] : 0.f);
+            if (!ignored) loss += lse - ((label >= 0 && label < C) ? x[label] : 0.f);
             correct += (arg == label) ? 1 : 0;
         }
     }
@@ -713,7 +738,7 @@ cross_entropy_kernel(const float* __restrict__ logits, long long ld, const long 
         float tl = 0.f;
         int tc = 0;
         for (int w = 0; w < nwarps; ++w) { tl += s_loss[w]; tc += s_correct[w]; }
-        out[0] = tl * inv_rows;
+        out[0] = nbad > 0 ? __int_as_float(0x7fc00000) : tl * inv_rows;
         out[1] = (float)tc;
     }
 }
@@ -896,7 +921,13 @@ extern "C" int vitk_colsum_f32(const float* x, long long ldx, long long rows, lo
 
 extern "C" int vitk_colsum_prod(const float* a, long long lda, const void* b_bf16, long long ldb, long long rows, int N,
                                 float* out, void* stream) {
-    if (rows <= 0 || N <= 0 || (N % 8) != 0 || (lda % 4) != 0 || (ldb % 8) != 0 || !a || !b_bf16 || !out)
+    return vitk_colsum_prod_ex(a, lda, b_bf16, ldb, rows, N, out, nullptr, 1, stream);
+}
+
+extern "C" int vitk_colsum_prod_ex(const float* a, long long lda, const void* b_bf16, long long ldb, long long rows,
+                                   int N, float* out, const float* rowscale, long long rows_per_sample, void* stream) {
+    if (rows <= 0 || N <= 0 || (N % 8) != 0 || (lda % 4) != 0 || (ldb % 8) != 0 || !a || !b_bf16 || !out ||
+        (rowscale != nullptr && rows_per_sample <= 0))
         return VITK_ERR_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int gx = (N + 255) / 256;
@@ -905,7 +936,7 @@ extern "C" int vitk_colsum_prod(const float* a, long long lda, const void* b_bf1
     if (gy > max_gy) gy = max_gy;
     if (gy < 1) gy = 1;
     colsum_prod_kernel<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(a, lda, reinterpret_cast<const __nv_bfloat16*>(b_bf16), ldb,
-                                                              rows, N, out);
+                                                              rows, N, out, rowscale, rows_per_sample);
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
 }
 

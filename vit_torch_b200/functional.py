@@ -97,7 +97,9 @@ def _dy_bf16(dy2d, M, D, gamma=None, rowscale=None, rows_per_sample=0):
 
 
 class BlockFn(torch.autograd.Function):
-    """x -> x + g1 * DropPath(Attn(LN1 x)) -> + g2 * DropPath(Mlp(LN2 .)); g1/g2 = None for plain ViT blocks."""
+    """x -> x + g1 * DropPath(Attn(LN1 x)) -> + g2 * DropPath(Mlp(LN2 .)); g1/g2 = None for plain ViT blocks.
+    `rowscale` = None or a pair (rs_attn, rs_mlp) of per-sample DropPath factors mask / keep_prob: the reference calls
+    drop_path once per branch (models/cait.py:148-149, timm Block), i.e. two independent draws."""
 
     @staticmethod
     def forward(ctx, x, num_heads, eps, scale, rowscale, n1w, n1b, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b,
@@ -111,6 +113,7 @@ class BlockFn(torch.autograd.Function):
         need_bwd = any(ctx.needs_input_grad)
         wqkv, wproj, wfc1, wfc2 = bf16_weight(qkvw), bf16_weight(projw), bf16_weight(fc1w), bf16_weight(fc2w)
         hidden = fc1w.shape[0]
+        rs1, rs2 = rowscale if rowscale is not None else (None, None)
 
         h1, mean1, rstd1 = ops.layernorm_fwd(x0, n1w, n1b, eps)
         qkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
@@ -135,7 +138,7 @@ class BlockFn(torch.autograd.Function):
         x1 = torch.empty((M, D), dtype=torch.float32, device=dev)
         f1 = torch.empty((M, D), dtype=torch.bfloat16, device=dev) if (g1 is not None and need_bwd) else None
         ops.gemm(o, wproj, epilogue=ops.EPI_RESID_F32, bias=projb, gamma=g1, resid=x0, out=x1, out2=f1,
-                 rowscale=rowscale, rows_per_sample=N)
+                 rowscale=rs1, rows_per_sample=N)
         h2, mean2, rstd2 = ops.layernorm_fwd(x1, n2w, n2b, eps)
         a = torch.empty((M, hidden), dtype=torch.bfloat16, device=dev) if need_bwd else None
         g = torch.empty((M, hidden), dtype=torch.bfloat16, device=dev)
@@ -143,11 +146,11 @@ class BlockFn(torch.autograd.Function):
         x2 = torch.empty((M, D), dtype=torch.float32, device=dev)
         f2 = torch.empty((M, D), dtype=torch.bfloat16, device=dev) if (g2 is not None and need_bwd) else None
         ops.gemm(g, wfc2, epilogue=ops.EPI_RESID_F32, bias=fc2b, gamma=g2, resid=x1, out=x2, out2=f2,
-                 rowscale=rowscale, rows_per_sample=N)
+                 rowscale=rs2, rows_per_sample=N)
 
         if need_bwd:
             ctx.save_for_backward(x0, mean1, rstd1, h1, qkv, o, lse2, x1, mean2, rstd2, h2, a, g, f1, f2, n1w, qkvw,
-                                  projw, n2w, fc1w, fc2w, g1, g2, rowscale, wqkv, wproj, wfc1, wfc2, S, Pm, rmax, rsum,
+                                  projw, n2w, fc1w, fc2w, g1, g2, rs1, rs2, wqkv, wproj, wfc1, wfc2, S, Pm, rmax, rsum,
                                   thl_w, thl_b, thw_w, thw_b)
             ctx.dims = (B, N, D, H, d, scale)
             ctx.has = (qkvb is not None, projb is not None, fc1b is not None, fc2b is not None)
@@ -158,7 +161,7 @@ class BlockFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         (x0, mean1, rstd1, h1, qkv, o, lse2, x1, mean2, rstd2, h2, a, g, f1, f2, n1w, qkvw, projw, n2w, fc1w, fc2w,
-         g1, g2, rowscale, wqkv, wproj, wfc1, wfc2, S, Pm, rmax, rsum, thl_w, thl_b, thw_w, thw_b) = ctx.saved_tensors
+         g1, g2, rs1, rs2, wqkv, wproj, wfc1, wfc2, S, Pm, rmax, rsum, thl_w, thl_b, thw_w, thw_b) = ctx.saved_tensors
         B, N, D, H, d, scale = ctx.dims
         M = B * N
         dev = dout.device
@@ -180,8 +183,8 @@ class BlockFn(torch.autograd.Function):
 
         # ---- Mlp branch: x2 = x1 + g2 * rowscale * (fc2(gelu(fc1(h2))))
         if dg2 is not None:
-            ops.colsum_prod_accum(dx2, f2, dg2)  # (rowscale == None whenever LayerScale models are built by the zoo)
-        dx2b = _dy_bf16(dx2, M, D, g2, rowscale, N)
+            ops.colsum_prod_accum(dx2, f2, dg2, rowscale=rs2, rows_per_sample=N)   # d_gamma = sum dY * rowscale * f
+        dx2b = _dy_bf16(dx2, M, D, g2, rs2, N)
         da = torch.empty((M, hidden), dtype=torch.bfloat16, device=dev)
         # fc2 dgrad with GELU' fused; the same epilogue reduces da over rows = fc1 bias gradient
         ops.gemm(dx2b, wfc2, b_mn=True, epilogue=ops.EPI_DGELU, aux=a, out=da, colsum=dfc1b)
@@ -199,13 +202,13 @@ class BlockFn(torch.autograd.Function):
             ops.gemm(da, h2, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dfc1w)
         del da
         # ---- LN2 backward + residual: dx1 = dx2 + LN2'(dh2); bf16 copy (x g1) feeds the proj dgrad/wgrad
-        plain1 = g1 is None and rowscale is None
+        plain1 = g1 is None and rs1 is None
         dx1, dx1b = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dx2, dweight=dn2w, dbias=dn2b, want_bf16=plain1,
                                       dxsum=dprojb if plain1 else None)
         if dg1 is not None:
-            ops.colsum_prod_accum(dx1, f1, dg1)
+            ops.colsum_prod_accum(dx1, f1, dg1, rowscale=rs1, rows_per_sample=N)
         if not plain1:
-            dx1b = ops.scale_cast(dx1, M, D, colscale=g1, rowscale=rowscale, rows_per_sample=N)
+            dx1b = ops.scale_cast(dx1, M, D, colscale=g1, rowscale=rs1, rows_per_sample=N)
         # ---- attention branch
         do = dh2  # reuse the buffer: dO [M, D] bf16
         ops.gemm(dx1b, wproj, b_mn=True, epilogue=ops.EPI_STORE_BF16, out=do)

@@ -84,8 +84,10 @@ class Block(nn.Module):
 
     def forward(self, x):
         rs = None
-        if isinstance(self.drop_path, DropPath):
-            rs = self.drop_path.rowscale(x.shape[0], x.device, self.training)
+        if isinstance(self.drop_path, DropPath) and self.training and self.drop_path.drop_prob > 0.0:
+            # one independent draw per residual branch, as the reference's two drop_path() calls
+            rs = (self.drop_path.rowscale(x.shape[0], x.device, True),
+                  self.drop_path.rowscale(x.shape[0], x.device, True))
         a, m = self.attn, self.mlp
         return Fn.BlockFn.apply(x, a.num_heads, self.norm1.eps, a.scale, rs, self.norm1.weight, self.norm1.bias,
                                 a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias, self.norm2.weight,

@@ -249,14 +249,14 @@ def cross_entropy(logits, labels, want_grad=True):
     return out2, dl
 
 
-def colsum_prod_accum(a, b, out):
-    """out[N] += sum_r a_f32[r, :] * b_bf16[r, :]."""
+def colsum_prod_accum(a, b, out, rowscale=None, rows_per_sample=1):
+    """out[N] += sum_r rowscale[r // rows_per_sample] * a_f32[r, :] * b_bf16[r, :]  (rowscale optional)."""
     global launch_count
-    _need_cuda(a, b, out)
+    _need_cuda(a, b, out, rowscale)
     assert a.dtype == torch.float32 and b.dtype == torch.bfloat16
     lib = _lib.load()
-    check(lib.vitk_colsum_prod(ptr(a), _ld(a), ptr(b), _ld(b), a.shape[0], a.shape[1], ptr(out), _stream()),
-          "vitk_colsum_prod")
+    check(lib.vitk_colsum_prod_ex(ptr(a), _ld(a), ptr(b), _ld(b), a.shape[0], a.shape[1], ptr(out), ptr(rowscale),
+                                  rows_per_sample, _stream()), "vitk_colsum_prod_ex")
     launch_count += 1
 
 

@@ -32,6 +32,7 @@ class _FusedMultiTensor(torch.optim.Optimizer):
         self._slot = 0
         self._hp_dev = {}     # group index -> device fp32 vector
         self._hp_host = {}    # group index -> last values written
+        self._cap = {}        # group index -> (pinned table, device table) owned by a CUDA-graph capture
 
     def _hyper(self, group) -> list:
         raise NotImplementedError
@@ -76,7 +77,41 @@ class _FusedMultiTensor(torch.optim.Optimizer):
         table = np.asarray(rows, dtype=np.int64).reshape(-1, ncol)
         cmap_dev = torch.tensor(cmap, dtype=torch.int32).view(-1, 2).to(dev)
         return dict(ids=[id(p) for p in ps], table=table, cmap=cmap_dev, nchunks=len(cmap), ws=ws,
+                    state_ptrs=self._state_ptrs(ps),
                     dev_table=torch.empty((len(ps), ncol), dtype=torch.int64, device=dev))
+
+    def _state_ptrs(self, ps):
+        return [tuple(self.state[p][nm].data_ptr() if nm in self.state[p] else 0 for nm in self._state_names)
+                for p in ps]
+
+    def prepare_capture(self) -> None:
+        """Call right before a CUDA-graph capture of step(): the captured step gets its OWN pinned staging buffer and
+        device pointer table, which no eager step() ever rewrites. (The graph holds the H2D copy of the table; with the
+        rotating buffers an eager step for another batch shape would, eight steps later, overwrite the buffer that copy
+        reads and every replay would then apply stale gradient pointers.) Allocation happens here because pinned /
+        device allocations are not allowed while a stream is capturing."""
+        self._cap = {}
+        for gi, group in enumerate(self.param_groups):
+            n = len(group["params"])
+            if n == 0:
+                continue
+            ncol = 4 + len(self._state_names)
+            dev = group["params"][0].device
+            self._cap[gi] = (torch.empty((n, ncol), dtype=torch.int64).pin_memory(),
+                             torch.empty((n, ncol), dtype=torch.int64, device=dev))
+
+    def load_state_dict(self, state_dict):
+        """torch replaces self.state with new tensors: the cached launch plans hold raw pointers into the old ones."""
+        super().load_state_dict(state_dict)
+        self._plan = {}
+        self._after_load()
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._plan = {}
+
+    def _after_load(self) -> None:
+        pass
 
     @staticmethod
     def _bf16_copy(p):
@@ -101,7 +136,8 @@ class _FusedMultiTensor(torch.optim.Optimizer):
                                              "(no CPU fallback)")
             plan = self._plan.get(gi)
             if (plan is None or plan["ids"] != [id(p) for p in ps]
-                    or any(self._bf16_copy(p) is not w for p, w in zip(ps, plan["ws"]))):
+                    or any(self._bf16_copy(p) is not w for p, w in zip(ps, plan["ws"]))
+                    or plan["state_ptrs"] != self._state_ptrs(ps)):
                 plan = self._plan[gi] = self._build_plan(ps, ps[0].device)
             tab = plan["table"]
             for t, p in enumerate(ps):
@@ -110,19 +146,28 @@ class _FusedMultiTensor(torch.optim.Optimizer):
                     g = p.grad = g.contiguous().float()
                 tab[t, 0] = p.data_ptr()
                 tab[t, 1] = g.data_ptr()
-            if len(self._pinned) < 8:
-                self._pinned.append(torch.empty(tab.shape, dtype=torch.int64).pin_memory())
-            pin = self._pinned[self._slot % len(self._pinned)]
-            self._slot += 1
-            if pin.shape != tab.shape:
-                pin = self._pinned[(self._slot - 1) % len(self._pinned)] = torch.empty(tab.shape,
-                                                                                       dtype=torch.int64).pin_memory()
+            capturing = torch.cuda.is_current_stream_capturing()
+            if capturing:
+                cap = self._cap.get(gi)
+                if cap is None or cap[0].shape[0] < tab.shape[0]:
+                    raise RuntimeError(f"{type(self).__name__}.step() under CUDA-graph capture needs prepare_capture() "
+                                       "first (capture-private pointer tables)")
+                pin, dev_table = cap[0][: tab.shape[0]], cap[1][: tab.shape[0]]
+            else:
+                if len(self._pinned) < 8:
+                    self._pinned.append(torch.empty(tab.shape, dtype=torch.int64).pin_memory())
+                pin = self._pinned[self._slot % len(self._pinned)]
+                self._slot += 1
+                if pin.shape != tab.shape:
+                    pin = self._pinned[(self._slot - 1) % len(self._pinned)] = torch.empty(
+                        tab.shape, dtype=torch.int64).pin_memory()
+                dev_table = plan["dev_table"]
             pin.numpy()[...] = tab
-            plan["dev_table"].copy_(pin, non_blocking=True)
+            dev_table.copy_(pin, non_blocking=True)
             hp = self._hp(gi, ps[0].device)
-            if not torch.cuda.is_current_stream_capturing():
+            if not capturing:
                 self.sync_hyper()     # (a capture records the launch only; the values are synced around it)
-            self._launch(plan, hp)
+            self._launch(dict(plan, dev_table=dev_table) if capturing else plan, hp)
         return loss
 
 
@@ -178,6 +223,10 @@ class FusedAdam(_FusedMultiTensor):
         plan = super()._build_plan(ps, dev)
         gi = next(i for i, g in enumerate(self.param_groups) if any(p is ps[0] for p in g["params"]))
         step = self._hp(gi, dev)[8]
+        loaded = [self.state[p].get("step") for p in ps]
+        loaded = [float(t) for t in loaded if t is not None and t.data_ptr() != step.data_ptr()]
+        if loaded:      # resumed from a state_dict: continue the bias corrections from the loaded step count
+            step.fill_(max(loaded))
         for p in ps:
             self.state[p]["step"] = step      # 0-d view of the group's device step counter
         return plan
@@ -205,8 +254,9 @@ class Trainer:
     ms/step -- and hung at process-group teardown; the arithmetic and launch sequence are those of the eager step)."""
 
     def __init__(self, model: nn.Module, lr: float = 1e-3, momentum: float = 0.9, reducer=None, fused_opt: bool = True,
-                 graph: bool = False, optimizer: str = "sgd"):
+                 graph: bool = False, optimizer: str = "sgd", strict_graph: bool = False):
         self.model = model
+        self.strict_graph = strict_graph    # True: a failed capture raises (bench.py) instead of falling back to eager
         self.reducer = reducer
         params = [p for p in model.parameters() if p.requires_grad]
         # `optimizer`: the reference's --opt names (utils_network.py:119-126); sgd / adam / adamw have fused kernels
@@ -264,6 +314,8 @@ class Trainer:
         from . import ops
         # (no warm-up step here: it would be an extra optimisation step; step() has already run two eager ones)
         self._sx, self._sy = x.clone(), y.clone()
+        if self.opt_in_graph and hasattr(self.opt, "prepare_capture"):
+            self.opt.prepare_capture()
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
         n0 = ops.launch_count
@@ -310,6 +362,8 @@ class Trainer:
             try:
                 self._capture(x, y)
             except Exception as exc:    # keep training: fall back to eager launches (same kernels, same collectives)
+                if self.strict_graph:
+                    raise
                 import sys
                 print(f"[vit_torch_b200] CUDA-graph capture of the step failed ({type(exc).__name__}: {exc}); "
                       "continuing with eager launches", file=sys.stderr)
