@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as Fn
-from .models import trunc_normal_
+from .models import load_pretrained, trunc_normal_
 from .modules import Block, DropPath, Mlp, PatchEmbed
 
 
@@ -178,25 +178,26 @@ class cait_models(nn.Module):
         return self.head(self.forward_features(x))
 
 
-# name -> (img_size, embed_dim, depth, num_heads, init_scale)   (models/cait.py:255-480)
+# name -> (img_size, embed_dim, depth, num_heads, init_scale, checkpoint file)   (models/cait.py:255-480)
 _SIZES = {
-    "cait_XXS24_224": (224, 192, 24, 4, 1e-5), "cait_XXS24": (384, 192, 24, 4, 1e-5),
-    "cait_XXS36_224": (224, 192, 36, 4, 1e-5), "cait_XXS36": (384, 192, 36, 4, 1e-5),
-    "cait_XS24": (384, 288, 24, 6, 1e-5), "cait_S24_224": (224, 384, 24, 8, 1e-5), "cait_S24": (384, 384, 24, 8, 1e-5),
-    "cait_S36": (384, 384, 36, 8, 1e-6), "cait_M36": (384, 768, 36, 16, 1e-6), "cait_M48": (448, 768, 48, 16, 1e-6),
+    "cait_XXS24_224": (224, 192, 24, 4, 1e-5, "XXS24_224.pth"), "cait_XXS24": (384, 192, 24, 4, 1e-5, "XXS24_384.pth"),
+    "cait_XXS36_224": (224, 192, 36, 4, 1e-5, "XXS36_224.pth"), "cait_XXS36": (384, 192, 36, 4, 1e-5, "XXS36_384.pth"),
+    "cait_XS24": (384, 288, 24, 6, 1e-5, "XS24_384.pth"), "cait_S24_224": (224, 384, 24, 8, 1e-5, "S24_224.pth"),
+    "cait_S24": (384, 384, 24, 8, 1e-5, "S24_384.pth"), "cait_S36": (384, 384, 36, 8, 1e-6, "S36_384.pth"),
+    "cait_M36": (384, 768, 36, 16, 1e-6, "M36_384.pth"), "cait_M48": (448, 768, 48, 16, 1e-6, "M48_448.pth"),
 }
 
 
 def _make(name):
-    img, dim, depth, heads, init = _SIZES[name]
+    img, dim, depth, heads, init, ckpt = _SIZES[name]
 
     def ctor(pretrained=False, **kwargs):
-        if pretrained:
-            raise RuntimeError("pretrained CaiT weights need network access; load a local state_dict instead "
-                               "(strip the 'module.' prefix as models/cait.py:264-273 does)")
         model = cait_models(img_size=img, patch_size=16, embed_dim=dim, depth=depth, num_heads=heads, mlp_ratio=4,
                             qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6), init_scale=init,
                             depth_token_only=2, **kwargs)
+        if pretrained:      # models/cait.py:264-273: checkpoint["model"]["module." + key]
+            load_pretrained(model, "https://dl.fbaipublicfiles.com/deit/" + ckpt, key="model", strip_prefix="module.",
+                            check_hash=True)
         return model
 
     ctor.__name__ = name

@@ -21,6 +21,21 @@ from . import functional as Fn
 from .modules import Block, PatchEmbed
 
 
+def load_pretrained(model, url, key=None, strip_prefix="", check_hash=False):
+    """The reference's / upstream's `pretrained=True` path: torch.hub.load_state_dict_from_url(url, map_location="cpu")
+    (models/cait.py:264-273, models/deit.py:100-105, DINO hubconf) and a strict load_state_dict. Works offline when the
+    file is already in $TORCH_HOME/hub/checkpoints/ (torch.hub only downloads what is not cached; TORCH_HOME is the
+    reference's --root_path, main.py:111); otherwise torch.hub raises its own download error, as the reference would.
+    `key`: sub-dict of the checkpoint ("model"); `strip_prefix`: e.g. "module." (CaiT checkpoints were saved from
+    DistributedDataParallel, models/cait.py:270-271)."""
+    ckpt = torch.hub.load_state_dict_from_url(url=url, map_location="cpu", check_hash=check_hash)
+    sd = ckpt[key] if key is not None else ckpt
+    if strip_prefix:
+        sd = {k: sd[strip_prefix + k] for k in model.state_dict().keys()}
+    model.load_state_dict(sd, strict=True)
+    return model
+
+
 def trunc_normal_(tensor, mean=0.0, std=1.0, a=-2.0, b=2.0):
     """Truncated-normal init used by DINO / timm / CaiT (`trunc_normal_(w, std=.02)`, models/cait.py:209-216)."""
     return nn.init.trunc_normal_(tensor, mean=mean, std=std, a=a, b=b)
@@ -98,12 +113,21 @@ class DinoVisionTransformer(nn.Module):
 _DINO = {"vits": dict(embed_dim=384, depth=12, num_heads=6), "vitb": dict(embed_dim=768, depth=12, num_heads=12)}
 
 
+# upstream hubconf.py checkpoint files (facebookresearch/dino@main)
+_DINO_URLS = {
+    ("vits", 16): "https://dl.fbaipublicfiles.com/dino/dino_deitsmall16_pretrain/dino_deitsmall16_pretrain.pth",
+    ("vits", 8): "https://dl.fbaipublicfiles.com/dino/dino_deitsmall8_pretrain/dino_deitsmall8_pretrain.pth",
+    ("vitb", 16): "https://dl.fbaipublicfiles.com/dino/dino_vitbase16_pretrain/dino_vitbase16_pretrain.pth",
+    ("vitb", 8): "https://dl.fbaipublicfiles.com/dino/dino_vitbase8_pretrain/dino_vitbase8_pretrain.pth",
+}
+
+
 def _dino(kind, patch, pretrained, **kw):
+    model = DinoVisionTransformer(patch_size=patch, num_classes=0, mlp_ratio=4, qkv_bias=True,
+                                  norm_layer=partial(nn.LayerNorm, eps=1e-6), **_DINO[kind], **kw)
     if pretrained:
-        raise RuntimeError("pretrained DINO weights need network access; load a local state_dict instead "
-                           "(parameter names match upstream)")
-    return DinoVisionTransformer(patch_size=patch, num_classes=0, mlp_ratio=4, qkv_bias=True,
-                                 norm_layer=partial(nn.LayerNorm, eps=1e-6), **_DINO[kind], **kw)
+        load_pretrained(model, _DINO_URLS[(kind, patch)])
+    return model
 
 
 def dino_vits16(pretrained=True, **kwargs):
@@ -177,12 +201,26 @@ class VisionTransformer(nn.Module):
         return self.head(x)
 
 
+# checkpoint files of models/deit.py:100-209
+_DEIT_URLS = {
+    (192, False, 224): "deit_tiny_patch16_224-a1311bcf.pth", (384, False, 224): "deit_small_patch16_224-cd65a155.pth",
+    (768, False, 224): "deit_base_patch16_224-b5f2ef4d.pth",
+    (192, True, 224): "deit_tiny_distilled_patch16_224-b40b3cf7.pth",
+    (384, True, 224): "deit_small_distilled_patch16_224-649709d9.pth",
+    (768, True, 224): "deit_base_distilled_patch16_224-df68dfff.pth",
+    (768, False, 384): "deit_base_patch16_384-8de9b5d1.pth",
+    (768, True, 384): "deit_base_distilled_patch16_384-d0272ac0.pth",
+}
+
+
 def _deit(embed_dim, num_heads, distilled, img_size=224, pretrained=False, **kw):
+    model = VisionTransformer(img_size=img_size, patch_size=16, embed_dim=embed_dim, depth=12, num_heads=num_heads,
+                              mlp_ratio=4, qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6),
+                              distilled=distilled, **kw)
     if pretrained:
-        raise RuntimeError("pretrained DeiT weights need network access; load a local state_dict instead")
-    return VisionTransformer(img_size=img_size, patch_size=16, embed_dim=embed_dim, depth=12, num_heads=num_heads,
-                             mlp_ratio=4, qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6),
-                             distilled=distilled, **kw)
+        load_pretrained(model, "https://dl.fbaipublicfiles.com/deit/" + _DEIT_URLS[(embed_dim, distilled, img_size)],
+                        key="model", check_hash=True)
+    return model
 
 
 def deit_tiny_patch16_224(pretrained=False, **kw):
