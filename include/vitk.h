@@ -140,6 +140,28 @@ int vitk_scale_cast(const float* x, long long rows_per_group, long long group_st
  * (Conv2d(C,D,P,P) + flatten(2).transpose(1,2); in-repo analogue models/swin.py:434,445). P % 4 == 0. */
 int vitk_patchify(const float* x, void* out_bf16, int B, int C, int H, int W, int P, void* stream);
 
+/*
+ * PatchEmbed as an im2col-free patch GEMM: Conv2d(C, D, kernel=P, stride=P)(x).flatten(2).transpose(1,2) + bias + pos
+ * written straight into the token buffer (DINO / timm PatchEmbed, call site models/vision_all.py:156,161-167; in-repo
+ * witness models/swin.py:434-445; token assembly models/cait.py:229-234, models/deit.py:35-43). The A operand is
+ * gathered by TMA from the NCHW image (rank-5 tensor map {px, pc, py, pr, c*b}); no [B*n, C*P*P] patch matrix exists.
+ *   img: fp32 [B,C,H,W] (tcgen05 kind::tf32 on the fp32 pixels and the fp32 weight) or bf16 [B,C,H,W] (kind::f16 with
+ *   the bf16 weight copy); weight [D, C*P*P] of the same type; bias fp32 [D] or null; pos fp32 [tok_N, ldpos];
+ *   out fp32 [B, tok_N, D]: out[b, tok_T + p, :] = patch_p . W^T + bias + pos[tok_T + p]. P * sizeof(elem) in {32,64,128}.
+ */
+int vitk_patch_embed_fwd(const void* img, int img_is_bf16, const void* weight, const float* bias, const float* pos,
+                         long long ldpos, float* out, int B, int C, int H, int W, int P, int D, int tok_N, int tok_T,
+                         void* stream);
+/* Its weight gradient (autograd of the conv): dW fp32 [D, C*P*P] += sum_{b,p} dY[b, tok_T+p, :]^T
+ * patch_p, with dY read in place from the token gradient [B, dy_tok_N, D] (same element type as img) and the patches
+ * gathered from the image again. Both operands are MN-major; images are split over thread blocks (red.global.add). */
+int vitk_patch_embed_wgrad(const void* img, int img_is_bf16, const void* dy, int dy_tok_N, int dy_tok_T, float* dW,
+                           int B, int C, int H, int W, int P, int D, void* stream);
+/* Device input pipeline: uint8 [B,C,H,W] -> bf16 (x/255 - mean[c]) / std[c], i.e. ToTensor + Normalize
+ * (utils_datasets.py:573-580) after the H2D copy of the raw bytes. H*W % 16 == 0. */
+int vitk_normalize_u8(const void* x_u8, void* y_bf16, const float* mean, const float* stdv, int B, int C, int H, int W,
+                      void* stream);
+
 /* out[b, t, :] = tok[t,:] + pos[t,:] for the T prefix tokens (cls, dist) of every image. */
 int vitk_prefix_tokens(const float* tok, const float* pos, float* out, int B, int T, long long tokens_per_image, int D,
                        void* stream);
@@ -171,6 +193,9 @@ int vitk_sgd_momentum_multi_hp(const void* table, const void* chunk_map, int num
  * `step` by one and derives the last two (bias corrections) on the device, so the step counter is graph-capturable.
  * Two launches. */
 int vitk_adam_multi(const void* table, const void* chunk_map, int num_chunks, float* hyper, void* stream);
+
+/* bf16 -> fp32 of n elements (gradients that travelled through a bf16 all-reduce back into the fp32 arena). */
+int vitk_cast_bf16_f32(const void* x_bf16, float* y, long long n, void* stream);
 
 /* fp32 -> bf16 cast of n elements (weights, activations). n % 8 == 0 not required. */
 int vitk_cast_f32_bf16(const float* x, void* y_bf16, long long n, void* stream);

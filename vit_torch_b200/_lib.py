@@ -37,9 +37,13 @@ SIGNATURES = {
     "vitk_colsum_prod_ex": [_P, _L, _P, _L, _L, _I, _P, _P, _L, _P],
     "vitk_scale_cast": [_P, _L, _L, _L, _I, _P, _P, _L, _P, _P],
     "vitk_patchify": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "vitk_patch_embed_fwd": [_P, _I, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "vitk_patch_embed_wgrad": [_P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    "vitk_normalize_u8": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "vitk_prefix_tokens": [_P, _P, _P, _I, _I, _L, _I, _P],
     "vitk_colsum_bf16": [_P, _L, _L, _I, _P, _P],
     "vitk_cast_f32_bf16": [_P, _P, _L, _P],
+    "vitk_cast_bf16_f32": [_P, _P, _L, _P],
     "vitk_sgd_chunk_elems": [],
     "vitk_sgd_momentum_multi": [_P, _P, _I, _F, _F, _F, _I, _P],
     "vitk_sgd_momentum_multi_hp": [_P, _P, _I, _P, _P],

@@ -164,7 +164,7 @@ class cait_models(nn.Module):
         B = x.shape[0]
         self.patch_embed.check(x)
         x = Fn.TokensFn.apply(x, self.patch_embed.proj.weight, self.patch_embed.proj.bias, self.pos_embed, None,
-                              self.patch_embed.patch_size[0])
+                              self.patch_embed.patch_size[0], self.patch_embed.norm_for(x))
         x = self.pos_drop(x)
         for blk in self.blocks:
             x = blk(x)

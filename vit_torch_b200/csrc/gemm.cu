@@ -186,6 +186,7 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
     g.tok_n = tok_n; g.tok_N = tok_N; g.tok_T = tok_T;
     g.nbatch_h = bt.nh; g.nbatch_b = bt.nb; g.so_h = bt.so_h; g.so_b = bt.so_b;
     g.colsum = colsum;
+    g.pe_G = 0; g.pe_rows = 0;
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("VITK_GEMM_DBG"); dbg = e ? atoi(e) : 0; }

@@ -50,6 +50,9 @@ struct GemmArgs {
     int tma_out;    // 1: `out` (and BIAS_GELU's second output) leave through TMA stores (tensor maps tmO / tmO2)
     int dbg;        // VITK_GEMM_DBG experiment switches (0 in production): 1 no L2 prefetch, 2 plain loads, 4 no loads, 8 no stores
     float* colsum;  // optional fp32 [N]: += column sums of the values stored to `out` (bias gradient of the next Linear)
+    // EPI_TOKENS_F32 behind the im2col-free PatchEmbed kernel (patch_embed.cu): an M tile is (image, group of pe_rpt patch
+    // rows), its first pe_rows rows are the patches pe_rows * group ... of that image. 0 = plain row-major patch rows.
+    int pe_G, pe_rows;
 };
 
 constexpr int GEMM_BM = 128;
@@ -221,8 +224,18 @@ template <int BN, int EPI> struct EpilogueWarp {
         R.out2 = nullptr; R.resid = nullptr; R.aux = nullptr;
         long long orow = row;  // output row
         if constexpr (EPI == EPI_TOKENS_F32) {
-            const long long bimg = row / g.tok_n;
-            const int pp = static_cast<int>(row - bimg * g.tok_n);
+            long long bimg;
+            int pp;
+            if (g.pe_G > 0) {   // tile = (image, patch-row group): tile row r is patch group * pe_rows + r of the image
+                const int r = quarter * 32 + lane;
+                bimg = m_tile / g.pe_G;
+                pp = (m_tile - (int)bimg * g.pe_G) * g.pe_rows + r;
+                R.ok = r < g.pe_rows && pp < g.tok_n;
+                if (!R.ok) pp = 0;
+            } else {
+                bimg = row / g.tok_n;
+                pp = static_cast<int>(row - bimg * g.tok_n);
+            }
             orow = bimg * g.tok_N + g.tok_T + pp;
             R.resid = g.resid + (long long)(g.tok_T + pp) * g.ldr + n0;  // pos_embed row
         } else if constexpr (EPI == EPI_RESID_F32) {

@@ -888,6 +888,28 @@ extern "C" int vitk_colsum_bf16(const void* x_bf16, long long ldx, long long row
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
 }
 
+namespace vitk {
+__global__ void __launch_bounds__(256)
+cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long n) {
+    const long long n8 = n / 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 v = ld_nc_v4(x + i * 8);
+        *reinterpret_cast<float4*>(y + i * 8) = make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+        *reinterpret_cast<float4*>(y + i * 8 + 4) = make_float4(bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w));
+    }
+    if (blockIdx.x == 0)
+        for (long long i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) y[i] = __bfloat162float(x[i]);
+}
+}  // namespace vitk
+
+extern "C" int vitk_cast_bf16_f32(const void* x_bf16, float* y, long long n, void* stream) {
+    if (n <= 0 || !x_bf16 || !y || ((reinterpret_cast<uintptr_t>(x_bf16) | reinterpret_cast<uintptr_t>(y)) & 15))
+        return VITK_ERR_ARG;
+    vitk::cast_bf16_f32_kernel<<<ew_grid(n / 8 + 1), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x_bf16), y, n);
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
 extern "C" int vitk_cast_f32_bf16(const float* x, void* y_bf16, long long n, void* stream) {
     if (n <= 0 || !x || !y_bf16) return VITK_ERR_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

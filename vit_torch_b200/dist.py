@@ -42,8 +42,10 @@ def configure_sm_partition(nccl_ctas: int = 4) -> None:
 
 
 class GradAllReducer:
-    def __init__(self, model: torch.nn.Module, process_group=None, overlap: bool = True):
+    def __init__(self, model: torch.nn.Module, process_group=None, overlap: bool = True, compress: bool = False):
         self.model = model
+        self.compress = bool(compress) and not overlap     # deferred mode only: bf16 gradients on the wire
+        self._wire = None
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.overlap = overlap
@@ -85,6 +87,24 @@ class GradAllReducer:
         """Forget bucket notifications (used after a CUDA-graph capture of backward: replays fire no hooks)."""
         self._pending.clear()
 
+    def _reduce_arena(self, arena):
+        """ONE collective over the used part of the gradient arena (average). compress: the arena is cast to bf16 by one
+        kernel, reduced in bf16 (half the bytes on NVLink) and cast back into the fp32 arena the optimiser reads."""
+        buf = arena.used()
+        if self.compress and self.cuda:
+            from . import ops
+            if self._wire is None or self._wire.numel() < buf.numel():
+                self._wire = torch.empty((arena.buf.numel(),), dtype=torch.bfloat16, device=buf.device)
+            wire = self._wire[: buf.numel()]
+            ops.cast_bf16(buf, out=wire)
+            dist.all_reduce(wire, op=dist.ReduceOp.AVG, group=self.pg)
+            ops.cast_f32_from_bf16(wire, buf)
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG if self.cuda else dist.ReduceOp.SUM, group=self.pg)
+            if not self.cuda:
+                buf.div_(self.world)
+        self.collectives += 1
+
     def finish_static(self, arena):
         """Deferred reduction without bucket notifications (the Trainer replays a captured forward + backward): one
         collective over the used part of the gradient arena, one over the gradients that live outside it."""
@@ -93,10 +113,7 @@ class GradAllReducer:
         op = dist.ReduceOp.AVG if self.cuda else dist.ReduceOp.SUM
         base = None
         if arena is not None and arena.off > 0:
-            dist.all_reduce(arena.used(), op=op, group=self.pg)
-            if not self.cuda:
-                arena.used().div_(self.world)
-            self.collectives += 1
+            self._reduce_arena(arena)
             base = arena.buf.untyped_storage().data_ptr()
         rest = [p.grad for p in self.model.parameters()
                 if p.grad is not None and (base is None or p.grad.untyped_storage().data_ptr() != base)]
@@ -129,10 +146,7 @@ class GradAllReducer:
         if (arena is not None and self._pending and all(w is None for _, w, _, _ in self._pending)
                 and all(b.untyped_storage().data_ptr() == arena.buf.untyped_storage().data_ptr()
                         for b, _, _, _ in self._pending)):
-            dist.all_reduce(arena.used(), op=dist.ReduceOp.AVG if self.cuda else dist.ReduceOp.SUM, group=self.pg)
-            self.collectives += 1
-            if not self.cuda:
-                arena.used().div_(self.world)
+            self._reduce_arena(arena)
             coalesced = True
         for buf, work, params, views in self._pending:
             if coalesced:
@@ -153,7 +167,9 @@ class GradAllReducer:
                 if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
                     p.grad.copy_(v)
         self._pending.clear()
-        rest = [p.grad for p in self.model.parameters() if p.grad is not None and id(p) not in covered]
+        abase = arena.buf.untyped_storage().data_ptr() if (coalesced and arena is not None) else None
+        rest = [p.grad for p in self.model.parameters() if p.grad is not None and id(p) not in covered
+                and (abase is None or p.grad.untyped_storage().data_ptr() != abase)]   # arena slices are reduced already
         if rest:
             flat = torch.cat([g.reshape(-1) for g in rest])
             dist.all_reduce(flat, op=dist.ReduceOp.AVG if self.cuda else dist.ReduceOp.SUM, group=self.pg)

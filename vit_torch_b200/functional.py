@@ -70,6 +70,18 @@ class GradArena:
 grad_arena: GradArena | None = None      # set by train.Trainer; None = every block allocates its own zero buffer
 
 
+def grad_zeros(shape, device):
+    """A zeroed fp32 gradient buffer: a slice of the step's gradient arena when there is one (zeroed by its single
+    memset, reduced by its single all-reduce), else a fresh tensor."""
+    n = 1
+    for v in shape:
+        n *= int(v)
+    buf = grad_arena.take((max(n, 4) + 3) // 4 * 4, device) if grad_arena is not None else None
+    if buf is None:
+        return torch.zeros(tuple(shape), dtype=torch.float32, device=device)
+    return buf[:n].view(tuple(shape))
+
+
 def _flat_grads(params, needs, device):
     """One contiguous fp32 zero buffer holding the gradients of all params that need one; returns views."""
     sizes = [p.numel() if (p is not None and need) else 0 for p, need in zip(params, needs)]
@@ -272,11 +284,26 @@ class BlockFn(torch.autograd.Function):
 grad_bucket_hooks: list = []
 
 
+def patch_embed_tma_ok(dtype, C, H, W, P) -> bool:
+    """Geometry the im2col-free PatchEmbed kernels take (patch_embed.cu): a patch row of P pixels must be 32 / 64 / 128
+    bytes (fp32: P = 8 / 16 / 32, bf16: P = 16 / 32 / 64) and one row of patches must fit a 64-row pipeline stage."""
+    import os
+    if os.environ.get("VITK_PATCH_EMBED", "tma") != "tma":
+        return False
+    esz = 4 if dtype == torch.float32 else 2
+    rb = P * esz
+    return (rb in (32, 64, 128) and W // P <= 64 and H // P <= 256 and (C * P) % (128 // rb) == 0
+            and (W * esz) % 16 == 0 and (H * W * esz) % 16 == 0)
+
+
 class TokensFn(torch.autograd.Function):
-    """PatchEmbed (Conv2d(C,D,P,P) as a patch GEMM) + prefix tokens + positional embedding -> [B, N, D] fp32."""
+    """PatchEmbed (Conv2d(C,D,P,P) as an im2col-free patch GEMM: TMA gathers the patches straight from NCHW) + prefix
+    tokens + positional embedding -> [B, N, D] fp32. img: fp32 (tf32 tensor-core path on the fp32 pixels and master
+    weight), bf16, or uint8 with `norm` = (mean[C], std[C]) device vectors (ToTensor + Normalize run on the device,
+    utils_datasets.py:573-580). Geometries the TMA path does not take fall back to an explicit patch matrix."""
 
     @staticmethod
-    def forward(ctx, img, conv_w, conv_b, pos, prefix, patch):
+    def forward(ctx, img, conv_w, conv_b, pos, prefix, patch, norm=None):
         B, C, Hh, Ww = img.shape
         D = conv_w.shape[0]
         P = patch
@@ -284,43 +311,69 @@ class TokensFn(torch.autograd.Function):
         T = 0 if prefix is None else prefix.shape[-2]
         N = n + T
         assert pos.shape[-2] == N and pos.shape[-1] == D, f"pos_embed {tuple(pos.shape)} vs tokens {N}x{D}"
-        x = img if img.dtype == torch.float32 else img.float()
-        patches = ops.patchify(x.contiguous(), P)
-        wb = bf16_weight(conv_w)
+        if img.dtype == torch.uint8:
+            if norm is None:
+                raise ValueError("uint8 images need the (mean, std) of the dataset's Normalize: "
+                                 "PatchEmbed.set_input_normalization(mean, std)")
+            x = ops.normalize_u8(img.contiguous(), norm[0], norm[1])
+        elif img.dtype in (torch.float32, torch.bfloat16):
+            x = img.contiguous()
+        else:
+            x = img.float().contiguous()
         pos2d = pos.detach().reshape(N, D).contiguous()
         out = torch.empty((B, N, D), dtype=torch.float32, device=img.device)
-        ops.gemm(patches, wb, epilogue=ops.EPI_TOKENS_F32, bias=conv_b, resid=pos2d, out=out.view(B * N, D),
-                 tok=(n, N, T))
+        tma = patch_embed_tma_ok(x.dtype, C, Hh, Ww, P)
+        patches = None
+        if tma:
+            w2d = conv_w.detach().reshape(D, -1) if x.dtype == torch.float32 else bf16_weight(conv_w)
+            ops.patch_embed_fwd(x, w2d.contiguous(), conv_b, pos2d, out, P, T)
+        else:
+            patches = ops.patchify(x if x.dtype == torch.float32 else x.float(), P)
+            ops.gemm(patches, bf16_weight(conv_w), epilogue=ops.EPI_TOKENS_F32, bias=conv_b, resid=pos2d,
+                     out=out.view(B * N, D), tok=(n, N, T))
         if T:
             ops.prefix_tokens(prefix.detach().reshape(T, D).contiguous(), pos2d, out, B, T, N, D)
-        ctx.save_for_backward(patches, conv_w, pos, prefix)
-        ctx.dims = (B, n, N, T, D, conv_b is not None)
+        ctx.save_for_backward(x if tma else patches, conv_w, pos, prefix)
+        ctx.dims = (B, n, N, T, D, conv_b is not None, P, tma)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        patches, conv_w, pos, prefix = ctx.saved_tensors
-        B, n, N, T, D, has_bias = ctx.dims
+        src, conv_w, pos, prefix = ctx.saved_tensors
+        B, n, N, T, D, has_bias, P, tma = ctx.dims
         needs = ctx.needs_input_grad
         dy = dout if dout.is_contiguous() else dout.contiguous()
         dev = dy.device
         dw = db = dpos = dprefix = None
-        if needs[3] or (needs[4] and T):
-            dp = torch.zeros((N * D,), dtype=torch.float32, device=dev)
+        want_db = needs[2] and has_bias
+        if needs[3] or (needs[4] and T) or (want_db and tma):
+            dp = grad_zeros((N * D,), dev)                                      # sum over the batch: d_pos
             ops.colsum_f32_accum(dy, N * D, B, N * D, dp)
             if needs[3]:
                 dpos = dp.view(pos.shape)
             if needs[4] and T:
-                dprefix = dp[:T * D].clone().view(prefix.shape)
-        if needs[1] or (needs[2] and has_bias):
+                dprefix = grad_zeros((T * D,), dev).copy_(dp[:T * D]).view(prefix.shape)
+            if want_db and tma:                                                # bias gradient = d_pos summed over patches
+                db = grad_zeros((D,), dev)
+                ops.colsum_f32_accum(dp[T * D:], D, n, D, db)
+        if tma:
+            if needs[1]:
+                dw = grad_zeros(conv_w.shape, dev)
+                if src.dtype == torch.float32:
+                    dyt = dy                                                    # fp32 token gradient read in place (tf32)
+                else:
+                    side = getattr(dout, "_vitk_bf16", None)
+                    dyt = side if side is not None and side.numel() == dy.numel() else ops.scale_cast(dy, B * N, D)
+                ops.patch_embed_wgrad(src, dyt.view(B, N, D), dw.view(D, -1), P, T)
+        elif needs[1] or want_db:
             dyb = ops.scale_cast(dy, B * n, D, rows_per_group=n, group_stride=N * D, offset_elems=T * D)
             if needs[1]:
-                dw = torch.zeros(conv_w.shape, dtype=torch.float32, device=dev)
-                ops.gemm(dyb, patches, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dw.view(D, -1))
-            if needs[2] and has_bias:
-                db = torch.zeros((D,), dtype=torch.float32, device=dev)
+                dw = grad_zeros(conv_w.shape, dev)
+                ops.gemm(dyb, src, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dw.view(D, -1))
+            if want_db:
+                db = grad_zeros((D,), dev)
                 ops.colsum_accum(dyb, db)
-        return None, dw, db, dpos, dprefix, None
+        return None, dw, db, dpos, dprefix, None, None
 
 
 class TokenNormFn(torch.autograd.Function):
@@ -342,8 +395,8 @@ class TokenNormFn(torch.autograd.Function):
         B, N, D, tok = ctx.dims
         dy = dy.contiguous().float()
         dx = torch.zeros((B, N, D), dtype=torch.float32, device=dy.device)
-        dw = torch.zeros((D,), dtype=torch.float32, device=dy.device)
-        db = torch.zeros((D,), dtype=torch.float32, device=dy.device)
+        dw = grad_zeros((D,), dy.device)
+        db = grad_zeros((D,), dy.device)
         ops.layernorm_bwd_rows(dy, xc.view(-1)[tok * D:], N * D, B, D, w, mean, rstd, dx=dx.view(-1)[tok * D:],
                                dx_stride=N * D, dweight=dw, dbias=db)
         return dx, dw, db, None, None
@@ -546,11 +599,11 @@ class HeadFn(torch.autograd.Function):
             n_out, k_in = ws[i].shape
             dyv = dyb[:, :n_out] if dyb.shape[1] != n_out else dyb
             if needs[2 + 2 * i]:
-                dw = torch.zeros((_pad8(n_out), k_in), dtype=torch.float32, device=dev)
+                dw = grad_zeros((_pad8(n_out), k_in), dev)
                 ops.gemm(dyv, ins[i], a_mn=True, b_mn=True, M=n_out, epilogue=ops.EPI_ATOMIC_F32, out=dw)
                 grads[2 * i] = dw[:n_out]
             if has_b[i] and needs[3 + 2 * i]:
-                db = torch.zeros((_pad8(n_out),), dtype=torch.float32, device=dev)
+                db = grad_zeros((_pad8(n_out),), dev)
                 ops.colsum_accum(dyb, db)
                 grads[2 * i + 1] = db[:n_out]
             if i > 0:

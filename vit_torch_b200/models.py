@@ -99,7 +99,8 @@ class DinoVisionTransformer(nn.Module):
         _, _, w, h = x.shape
         P = self.patch_embed.patch_size[0]
         pos = self.interpolate_pos_encoding((w // P) * (h // P), w, h)
-        x = Fn.TokensFn.apply(x, self.patch_embed.proj.weight, self.patch_embed.proj.bias, pos, self.cls_token, P)
+        x = Fn.TokensFn.apply(x, self.patch_embed.proj.weight, self.patch_embed.proj.bias, pos, self.cls_token, P,
+                              self.patch_embed.norm_for(x))
         return self.pos_drop(x)
 
     def forward(self, x):
@@ -186,7 +187,7 @@ class VisionTransformer(nn.Module):
         self.patch_embed.check(x)
         prefix = self.cls_token if self.dist_token is None else torch.cat((self.cls_token, self.dist_token), dim=1)
         x = Fn.TokensFn.apply(x, self.patch_embed.proj.weight, self.patch_embed.proj.bias, self.pos_embed, prefix,
-                              self.patch_embed.patch_size[0])
+                              self.patch_embed.patch_size[0], self.patch_embed.norm_for(x))
         x = self.pos_drop(x)
         x = self.blocks(x)
         cls = Fn.TokenNormFn.apply(x, self.norm.weight, self.norm.bias, self.norm.eps, 0)

@@ -105,6 +105,24 @@ class PatchEmbed(nn.Module):
         self.num_patches = (self.img_size[0] // self.patch_size[0]) * (self.img_size[1] // self.patch_size[1])
         self.strict_size = strict_size
         self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+        self.input_norm = None   # (mean[C], std[C]) device vectors: uint8 images are normalised on the device
+
+    def set_input_normalization(self, mean, std):
+        """Device input pipeline: feed raw uint8 [B,C,H,W] images; ToTensor + Normalize(mean, std)
+        (utils_datasets.py:573-580) run on the GPU in front of the patch GEMM. Not part of the state_dict."""
+        dev = self.proj.weight.device
+        self.input_norm = (torch.as_tensor(mean, dtype=torch.float32, device=dev).contiguous(),
+                           torch.as_tensor(std, dtype=torch.float32, device=dev).contiguous())
+        return self
+
+    def norm_for(self, x):
+        if x.dtype != torch.uint8:
+            return None
+        if self.input_norm is None:
+            raise ValueError("uint8 input: call patch_embed.set_input_normalization(mean, std) first")
+        if self.input_norm[0].device != x.device:
+            self.input_norm = tuple(t.to(x.device) for t in self.input_norm)
+        return self.input_norm
 
     def check(self, x):
         P = self.patch_size[0]
@@ -123,4 +141,5 @@ class PatchEmbed(nn.Module):
         D = self.proj.out_channels
         n = (x.shape[-2] // self.patch_size[0]) * (x.shape[-1] // self.patch_size[0])
         zero_pos = torch.zeros((1, n, D), dtype=torch.float32, device=x.device)
-        return Fn.TokensFn.apply(x, self.proj.weight, self.proj.bias, zero_pos, None, self.patch_size[0])
+        return Fn.TokensFn.apply(x, self.proj.weight, self.proj.bias, zero_pos, None, self.patch_size[0],
+                                 self.norm_for(x))

@@ -149,6 +149,16 @@ def cast_bf16(x, out=None):
     return out
 
 
+def cast_f32_from_bf16(x, out):
+    """bf16 -> fp32 copy into `out` (same number of elements)."""
+    global launch_count
+    _need_cuda(x, out)
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.float32 and x.numel() == out.numel()
+    check(_lib.load().vitk_cast_bf16_f32(ptr(x), ptr(out), x.numel(), _stream()), "vitk_cast_bf16_f32")
+    launch_count += 1
+    return out
+
+
 def attn_fwd(qkv, B, N, H, d, scale):
     """qkv bf16 [B*N, 3*H*d] -> (out bf16 [B*N, H*d], lse2 fp32 [B, H, N])."""
     global launch_count
@@ -289,6 +299,45 @@ def patchify(x, P):
     return out
 
 
+def patch_embed_fwd(img, weight, bias, pos2d, out, P, T):
+    """out[b, T + p, :] = patch_p . weight^T + bias + pos2d[T + p]; img fp32 / bf16 [B,C,H,W] (TMA gather from NCHW),
+    weight [D, C*P*P] of img's dtype, out fp32 [B, N, D]."""
+    global launch_count
+    _need_cuda(img, weight, pos2d, out)
+    assert img.is_contiguous() and weight.is_contiguous() and img.dtype == weight.dtype
+    assert img.dtype in (torch.float32, torch.bfloat16)
+    B, C, H, W = img.shape
+    D = weight.shape[0]
+    check(_lib.load().vitk_patch_embed_fwd(ptr(img), int(img.dtype == torch.bfloat16), ptr(weight), ptr(bias), ptr(pos2d),
+                                           pos2d.stride(0), ptr(out), B, C, H, W, P, D, out.shape[1], T, _stream()),
+          "vitk_patch_embed_fwd")
+    launch_count += 1
+    return out
+
+
+def patch_embed_wgrad(img, dy, dw, P, T):
+    """dw fp32 [D, C*P*P] += sum_{b,p} dy[b, T + p, :]^T patch_p; dy [B, N, D] of img's dtype."""
+    global launch_count
+    _need_cuda(img, dy, dw)
+    assert img.is_contiguous() and dy.is_contiguous() and img.dtype == dy.dtype and dw.dtype == torch.float32
+    B, C, H, W = img.shape
+    check(_lib.load().vitk_patch_embed_wgrad(ptr(img), int(img.dtype == torch.bfloat16), ptr(dy), dy.shape[1], T, ptr(dw),
+                                             B, C, H, W, P, dy.shape[2], _stream()), "vitk_patch_embed_wgrad")
+    launch_count += 1
+
+
+def normalize_u8(x, mean, std):
+    """uint8 [B,C,H,W] -> bf16 (x/255 - mean[c]) / std[c] (ToTensor + Normalize on the device)."""
+    global launch_count
+    _need_cuda(x, mean, std)
+    assert x.dtype == torch.uint8 and x.is_contiguous() and mean.dtype == torch.float32 and std.dtype == torch.float32
+    B, C, H, W = x.shape
+    y = torch.empty((B, C, H, W), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().vitk_normalize_u8(ptr(x), ptr(y), ptr(mean), ptr(std), B, C, H, W, _stream()), "vitk_normalize_u8")
+    launch_count += 1
+    return y
+
+
 def prefix_tokens(tok, pos, out, B, T, tokens_per_image, D):
     """out[b, t, :] = tok[t] + pos[t] for t < T."""
     global launch_count
@@ -409,7 +458,7 @@ def _timed(fn):
 
 for _name in ("gemm", "gemm_batched", "layernorm_fwd", "layernorm_bwd", "layernorm_fwd_rows", "layernorm_bwd_rows",
               "colsum_accum", "colsum_f32_accum", "colsum_prod_accum", "cast_bf16", "attn_fwd", "attn_bwd", "scale_cast",
-              "patchify", "prefix_tokens", "th_mix_fwd", "th_mix_bwd", "class_attn_fwd", "class_attn_bwd"):
+              "patchify", "prefix_tokens", "patch_embed_fwd", "patch_embed_wgrad", "normalize_u8", "th_mix_fwd", "th_mix_bwd", "class_attn_fwd", "class_attn_bwd"):
     globals()[_name] = _timed(globals()[_name])
 
 
