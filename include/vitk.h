@@ -147,14 +147,15 @@ int vitk_patchify(const float* x, void* out_bf16, int B, int C, int H, int W, in
  * gathered by TMA from the NCHW image (rank-5 tensor map {px, pc, py, pr, c*b}); no [B*n, C*P*P] patch matrix exists.
  *   img: fp32 [B,C,H,W] (tcgen05 kind::tf32 on the fp32 pixels and the fp32 weight) or bf16 [B,C,H,W] (kind::f16 with
  *   the bf16 weight copy); weight [D, C*P*P] of the same type; bias fp32 [D] or null; pos fp32 [tok_N, ldpos];
- *   out fp32 [B, tok_N, D]: out[b, tok_T + p, :] = patch_p . W^T + bias + pos[tok_T + p]. P * sizeof(elem) in {32,64,128}.
+ *   out fp32 [B, tok_N, D]: out[b, tok_T + p, :] = patch_p . W^T + bias + pos[tok_T + p]. P * sizeof(elem) in {16,32,64,128}.
  */
 int vitk_patch_embed_fwd(const void* img, int img_is_bf16, const void* weight, const float* bias, const float* pos,
                          long long ldpos, float* out, int B, int C, int H, int W, int P, int D, int tok_N, int tok_T,
                          void* stream);
 /* Its weight gradient (autograd of the conv): dW fp32 [D, C*P*P] += sum_{b,p} dY[b, tok_T+p, :]^T
- * patch_p, with dY read in place from the token gradient [B, dy_tok_N, D] (same element type as img) and the patches
- * gathered from the image again. Both operands are MN-major; images are split over thread blocks (red.global.add). */
+ * patch_p, with dY read in place from a bf16 token gradient [B, dy_tok_N, D] and the patches gathered from the bf16
+ * image again (img_is_bf16 must be 1: MN-major tf32 operands need 128-byte rows, so fp32 images are cast once by the
+ * caller). Both operands are MN-major; images are split over thread blocks (red.global.add). */
 int vitk_patch_embed_wgrad(const void* img, int img_is_bf16, const void* dy, int dy_tok_N, int dy_tok_T, float* dW,
                            int B, int C, int H, int W, int P, int D, void* stream);
 /* Device input pipeline: uint8 [B,C,H,W] -> bf16 (x/255 - mean[c]) / std[c], i.e. ToTensor + Normalize
@@ -244,6 +245,14 @@ int vitk_th_mix_fwd(const float* S, const float* wl, const float* bl, const floa
 int vitk_th_mix_bwd(const float* S, const float* dPm, const float* rowmax, const float* rowsum, const float* wl,
                     const float* bl, const float* ww, const float* bw, float scale, void* dS_bf16, float* dwl, float* dbl,
                     float* dww, float* dbw, int B, int H, int N, int Np, void* stream);
+/* Version 2 of the mixing kernels (one warp per query row, every head mix and the weight-gradient products on the
+ * tensor cores through mma.sync tf32, 3xTF32 for the logits) serves rows of up to 208 keys: vitk_th_mix_fwd picks it
+ * by itself; its backward takes dP' in bf16 (half the traffic of the fp32 form). vitk_th_mix_supports_bf16_dp(Np)
+ * returns 1 when that backward is available for rows of pitch Np. */
+int vitk_th_mix_supports_bf16_dp(int Np);
+int vitk_th_mix_bwd_bf16(const float* S, const void* dPm_bf16, const float* rowmax, const float* rowsum, const float* wl,
+                         const float* bl, const float* ww, const float* bw, float scale, void* dS_bf16, float* dwl,
+                         float* dbl, float* dww, float* dbw, int B, int H, int N, int Np, void* stream);
 
 /*
  * CaiT class attention (models/cait.py:38-55): one query row per (image, head). q bf16 [B,C] (unscaled), keys/values:

@@ -51,6 +51,8 @@ SIGNATURES = {
     "vitk_attn_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "vitk_th_mix_fwd": [_P, _P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _P],
     "vitk_th_mix_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "vitk_th_mix_supports_bf16_dp": [_I],
+    "vitk_th_mix_bwd_bf16": [_P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "vitk_class_attn_fwd": [_P, _P, _P, _P, _P, _L, _L, _F, _P, _P, _I, _I, _I, _I, _P],
     "vitk_class_attn_bwd": [_P, _P, _P, _P, _P, _L, _L, _P, _P, _F, _P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _I, _P],
     "vitk_attn_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],

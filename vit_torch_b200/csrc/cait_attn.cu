@@ -9,7 +9,9 @@
 //    GEMV - softmax - GEMV, forward and backward.
 #include "common.cuh"
 #include "tmap.cuh"
+#include "th_mix2.cuh"
 #include "../../include/vitk.h"
+#include <stdlib.h>
 
 namespace vitk {
 
@@ -447,6 +449,58 @@ template <int H> static int th_bwd_launch(const float* S, const float* dPm, cons
 
 using namespace vitk;
 
+// version 2 (warp per row, tensor-core head mixes) takes rows of up to 16 * TH2_MAX_TILES keys; VITK_TH_MIX=1 forces v1
+static bool th2_enabled(int Np) {
+    static int v1 = -1;
+    if (v1 < 0) { const char* e = getenv("VITK_TH_MIX"); v1 = (e != nullptr && e[0] == '1') ? 1 : 0; }
+    return !v1 && Np <= 16 * TH2_MAX_TILES;
+}
+template <int H> static int th2_fwd_launch(const float* S, const float* wl, const float* bl, const float* ww,
+                                           const float* bw, float scale, __nv_bfloat16* Pm, float* rmax, float* rsum,
+                                           int B, int N, int Np, cudaStream_t st) {
+    const long long rows = (long long)B * N;
+    long long grid = (rows + TH2_WARPS - 1) / TH2_WARPS;
+    const long long cap = (long long)sm_count() * 4;
+    if (grid > cap) grid = cap;
+    th_mix2_fwd_kernel<H><<<(unsigned)grid, TH2_WARPS * 32, 0, st>>>(S, wl, bl, ww, bw, scale, Pm, rmax, rsum, B, N, Np);
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+template <int H> static int th2_bwd_launch(const float* S, const __nv_bfloat16* dPm, const float* rmax, const float* rsum,
+                                           const float* wl, const float* bl, const float* ww, float scale,
+                                           __nv_bfloat16* dS, float* dwl, float* dbl, float* dww, float* dbw, int B, int N,
+                                           int Np, cudaStream_t st) {
+    const long long rows = (long long)B * N;
+    long long grid = (rows + TH2_WARPS - 1) / TH2_WARPS;
+    const long long cap = (long long)sm_count() * 1;      // 1 block / SM (register budget); persistent over rows
+    if (grid > cap) grid = cap;
+    th_mix2_bwd_kernel<H><<<(unsigned)grid, TH2_WARPS * 32, 0, st>>>(S, dPm, rmax, rsum, wl, bl, ww, scale, dS, dwl, dbl,
+                                                                    dww, dbw, B, N, Np);
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
+extern "C" int vitk_th_mix_supports_bf16_dp(int Np) { return th2_enabled(Np) ? 1 : 0; }
+
+extern "C" int vitk_th_mix_bwd_bf16(const float* S, const void* dPm_bf16, const float* rowmax, const float* rowsum,
+                                    const float* wl, const float* bl, const float* ww, const float* bw, float scale,
+                                    void* dS_bf16, float* dwl, float* dbl, float* dww, float* dbw, int B, int H, int N,
+                                    int Np, void* stream) {
+    if (B <= 0 || N <= 0 || Np < N || (Np % 8) != 0 || !S || !dPm_bf16 || !rowmax || !rowsum || !wl || !bl || !ww || !bw ||
+        !dS_bf16 || !dwl || !dbl || !dww || !dbw)
+        return VITK_ERR_ARG;
+    if (!th2_enabled(Np)) return VITK_ERR_UNSUPPORTED;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    auto dP = reinterpret_cast<const __nv_bfloat16*>(dPm_bf16);
+    auto dS = reinterpret_cast<__nv_bfloat16*>(dS_bf16);
+    switch (H) {
+        case 2: return th2_bwd_launch<2>(S, dP, rowmax, rowsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
+        case 4: return th2_bwd_launch<4>(S, dP, rowmax, rowsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
+        case 6: return th2_bwd_launch<6>(S, dP, rowmax, rowsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
+        case 8: return th2_bwd_launch<8>(S, dP, rowmax, rowsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
+        case 16: return th2_bwd_launch<16>(S, dP, rowmax, rowsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
+        default: return VITK_ERR_UNSUPPORTED;
+    }
+}
+
 extern "C" int vitk_th_mix_fwd(const float* S, const float* wl, const float* bl, const float* ww, const float* bw,
                                float scale, void* Pm_bf16, float* rowmax, float* rowsum, int B, int H, int N, int Np,
                                void* stream) {
@@ -454,6 +508,16 @@ extern "C" int vitk_th_mix_fwd(const float* S, const float* wl, const float* bl,
         return VITK_ERR_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     auto P = reinterpret_cast<__nv_bfloat16*>(Pm_bf16);
+    if (th2_enabled(Np)) {
+        switch (H) {
+            case 2: return th2_fwd_launch<2>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);
+            case 4: return th2_fwd_launch<4>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);
+            case 6: return th2_fwd_launch<6>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);
+            case 8: return th2_fwd_launch<8>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);
+            case 16: return th2_fwd_launch<16>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);
+            default: return VITK_ERR_UNSUPPORTED;
+        }
+    }
     switch (H) {
         case 4: return th_fwd_launch<4>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);
         case 6: return th_fwd_launch<6>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);

@@ -47,7 +47,9 @@ __device__ __forceinline__ uint64_t pe_smem_desc(uint32_t saddr, uint32_t lbo, u
     d |= static_cast<uint64_t>(layout) << 61;
     return d;
 }
-__device__ __forceinline__ uint32_t pe_layout_of(int rb) { return rb == 128 ? 2u : (rb == 64 ? 4u : 6u); }
+// UMMA layout type of a tile whose rows are rb bytes: 128B / 64B / 32B swizzle; 16-byte rows use the unswizzled
+// ("interleaved") canonical layout, where 8 consecutive 16-byte rows form one core matrix
+__device__ __forceinline__ uint32_t pe_layout_of(int rb) { return rb == 128 ? 2u : (rb == 64 ? 4u : (rb == 32 ? 6u : 0u)); }
 
 template <typename T>
 __device__ __forceinline__ void pe_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -155,7 +157,7 @@ patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_c
         if (lane == 0) {
             constexpr uint32_t idesc = pe_idesc(E::FMT, GEMM_BM, PE_BN, 0, 0);
             const uint32_t a_layout = pe_layout_of(pe.RB);
-            const int mma_per_sub = pe.RB / 32;   // each MMA consumes 32 bytes of k per row
+            const int mma_per_sub = pe.RB >= 32 ? pe.RB / 32 : 1;   // each MMA consumes 32 bytes of k per row
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
@@ -171,9 +173,15 @@ patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_c
                     const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + stage * PE_B_BYTES), 0, 1024);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int sub = i / mma_per_sub, within = i - sub * mma_per_sub;
-                        const uint64_t adesc =
-                            pe_smem_desc(sa + sub * a_sub_bytes + within * 32, 0, 8 * pe.RB, a_layout);
+                        uint64_t adesc;
+                        if (pe.RB >= 32) {
+                            const int sub = i / mma_per_sub, within = i - sub * mma_per_sub;
+                            adesc = pe_smem_desc(sa + sub * a_sub_bytes + within * 32, 0, 8 * pe.RB, a_layout);
+                        } else {
+                            // 16-byte patch rows: the two 16-byte K chunks of one MMA are image rows py, py+1 = two
+                            // sub-tiles (LBO apart); 8 patches = one 128-byte core matrix (SBO apart)
+                            adesc = pe_smem_desc(sa + 2 * i * a_sub_bytes, (uint32_t)a_sub_bytes, 128, 0u);
+                        }
                         pe_umma<T>(tmem_d, adesc, bdesc + i * 2, idesc, (ks > 0 || i > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);
@@ -315,7 +323,10 @@ patch_embed_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_
                 for (int k = 0; k < w.ksteps; ++k) {
                     // MN-major: LBO = distance between MN chunks, SBO = distance between 8-row k groups
                     const uint64_t adesc = pe_smem_desc(sa + k * a_kstep, WG_ROWS * 128, 8 * 128, 2u);
-                    const uint64_t bdesc = pe_smem_desc(sb + k * b_kstep, (uint32_t)b_chunk, 8 * pe.RB, b_layout);
+                    // (unswizzled 16-byte rows: the descriptor's two offsets swap roles, see make_umma_desc<Major::MN>)
+                    const uint64_t bdesc = pe.RB >= 32
+                                               ? pe_smem_desc(sb + k * b_kstep, (uint32_t)b_chunk, 8 * pe.RB, b_layout)
+                                               : pe_smem_desc(sb + k * b_kstep, 8 * pe.RB, (uint32_t)b_chunk, 0u);
                     pe_umma<T>(tmem_base, adesc, bdesc, idesc, (it > it0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[stage]);
@@ -389,14 +400,15 @@ static int make_img_tmap(CUtensorMap* tm, const void* img, int esz, CUtensorMapD
     uint32_t box[5] = {(uint32_t)P, (uint32_t)Wp, 1u, (uint32_t)rpt, 1u};
     const int rb = P * esz;
     const CUtensorMapSwizzle sw = rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                            : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+                                  : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                              : (rb == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
     return make_tmap(tm, img, 5, dims, strides, box, sw, dt);
 }
 
 static bool pe_geom(PeGeom& pe, int B, int C, int H, int W, int P, int esz, int max_rows) {
     if (B <= 0 || C <= 0 || P <= 0 || H % P || W % P) return false;
     const int rb = P * esz;
-    if (!(rb == 32 || rb == 64 || rb == 128)) return false;
+    if (!(rb == 16 || rb == 32 || rb == 64 || rb == 128)) return false;
     pe.B = B; pe.C = C; pe.P = P; pe.Hp = H / P; pe.Wp = W / P;
     if (pe.Wp > max_rows || pe.Wp > 256 || pe.Hp > 256) return false;
     pe.RB = rb; pe.KPS = 128 / rb;
@@ -520,8 +532,10 @@ extern "C" int vitk_patch_embed_wgrad(const void* img, int img_is_bf16, const vo
     if (!img || !dy || !dW || ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(dy)) & 15))
         return VITK_ERR_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (img_is_bf16) return pe_wgrad_launch<__nv_bfloat16>(img, dy, dy_tok_N, dy_tok_T, dW, B, C, H, W, P, D, st);
-    return pe_wgrad_launch<float>(img, dy, dy_tok_N, dy_tok_T, dW, B, C, H, W, P, D, st);
+    // tcgen05 reads MN-major tf32 operands only in the 128B_BASE32B layout, which needs 128-byte patch rows: the weight
+    // gradient runs in bf16 (the caller casts an fp32 image / gradient once; still no patch matrix)
+    if (!img_is_bf16) return VITK_ERR_UNSUPPORTED;
+    return pe_wgrad_launch<__nv_bfloat16>(img, dy, dy_tok_N, dy_tok_T, dW, B, C, H, W, P, D, st);
 }
 
 extern "C" int vitk_normalize_u8(const void* x_u8, void* y_bf16, const float* mean, const float* stdv, int B, int C,

@@ -239,9 +239,10 @@ class BlockFn(torch.autograd.Function):
             dthl_b = dthl_b if dthl_b is not None else zeros(thl_b)
             dthw_w = dthw_w if dthw_w is not None else zeros(thw_w)
             dthw_b = dthw_b if dthw_b is not None else zeros(thw_b)
-            dPm = torch.empty((B, H, N, Np), dtype=torch.float32, device=dev)      # dP'[i,j] = dO_i . v_j
+            dp16 = ops.th_mix_bf16_dp(Np)       # version-2 mixing kernels read dP' in bf16
+            dPm = torch.empty((B, H, N, Np), dtype=torch.bfloat16 if dp16 else torch.float32, device=dev)
             ops.gemm_batched(do, D, d, N * D, False, qkv, 3 * D, d, N * 3 * D, False, N, N, d, H, B, dPm, Np, N * Np,
-                             H * N * Np, b_off=2 * D, out_f32=True)
+                             H * N * Np, b_off=2 * D, out_f32=not dp16)     # dP'[i,j] = dO_i . v_j
             dqkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
             ops.gemm_batched(Pm, Np, N * Np, H * N * Np, True, do, D, d, N * D, True, N, d, N, H, B, dqkv, 3 * D, d,
                              N * 3 * D, out_off=2 * D)                              # dV = P'^T dO
@@ -285,14 +286,14 @@ grad_bucket_hooks: list = []
 
 
 def patch_embed_tma_ok(dtype, C, H, W, P) -> bool:
-    """Geometry the im2col-free PatchEmbed kernels take (patch_embed.cu): a patch row of P pixels must be 32 / 64 / 128
-    bytes (fp32: P = 8 / 16 / 32, bf16: P = 16 / 32 / 64) and one row of patches must fit a 64-row pipeline stage."""
+    """Geometry the im2col-free PatchEmbed kernels take (patch_embed.cu): a patch row of P pixels must be 16 / 32 / 64 /
+    128 bytes (fp32: P = 4..32, bf16: P = 8..64) and one row of patches must fit a 64-row pipeline stage."""
     import os
     if os.environ.get("VITK_PATCH_EMBED", "tma") != "tma":
         return False
     esz = 4 if dtype == torch.float32 else 2
     rb = P * esz
-    return (rb in (32, 64, 128) and W // P <= 64 and H // P <= 256 and (C * P) % (128 // rb) == 0
+    return (rb in (16, 32, 64, 128) and W // P <= 64 and H // P <= 256 and (C * P) % (128 // rb) == 0
             and (W * esz) % 16 == 0 and (H * W * esz) % 16 == 0)
 
 
@@ -359,12 +360,12 @@ class TokensFn(torch.autograd.Function):
         if tma:
             if needs[1]:
                 dw = grad_zeros(conv_w.shape, dev)
-                if src.dtype == torch.float32:
-                    dyt = dy                                                    # fp32 token gradient read in place (tf32)
-                else:
-                    side = getattr(dout, "_vitk_bf16", None)
-                    dyt = side if side is not None and side.numel() == dy.numel() else ops.scale_cast(dy, B * N, D)
-                ops.patch_embed_wgrad(src, dyt.view(B, N, D), dw.view(D, -1), P, T)
+                # the weight gradient runs in bf16 (tcgen05 has no MN-major tf32 form for 64-byte rows): an fp32
+                # image is cast once (NCHW -> NCHW, not a patch matrix); the bf16 token gradient usually exists already
+                img16 = src if src.dtype == torch.bfloat16 else ops.cast_bf16(src)
+                side = getattr(dout, "_vitk_bf16", None)
+                dyt = side if side is not None and side.numel() == dy.numel() else ops.scale_cast(dy, B * N, D)
+                ops.patch_embed_wgrad(img16, dyt.view(B, N, D), dw.view(D, -1), P, T)
         elif needs[1] or want_db:
             dyb = ops.scale_cast(dy, B * n, D, rows_per_group=n, group_stride=N * D, offset_elems=T * D)
             if needs[1]:

@@ -380,12 +380,24 @@ def th_mix_fwd(S, wl, bl, ww, bw, scale, B, H, N, Np):
     return Pm, rmax, rsum
 
 
+def th_mix_bf16_dp(Np) -> bool:
+    """True when the talking-heads backward takes dP' in bf16 (version-2 kernels, rows of up to 208 keys)."""
+    return bool(_lib.load().vitk_th_mix_supports_bf16_dp(int(Np)))
+
+
 def th_mix_bwd(S, dPm, rmax, rsum, wl, bl, ww, bw, scale, dwl, dbl, dww, dbw, B, H, N, Np):
-    """Talking-heads mixing backward -> dS bf16 [B,H,N,Np]; accumulates into dwl/dbl/dww/dbw."""
+    """Talking-heads mixing backward -> dS bf16 [B,H,N,Np]; accumulates into dwl/dbl/dww/dbw. dPm fp32, or bf16 when
+    th_mix_bf16_dp(Np)."""
     global launch_count
     _need_cuda(S, dPm)
     dS = torch.empty((B, H, N, Np), dtype=torch.bfloat16, device=S.device)
     lib = _lib.load()
+    if dPm.dtype == torch.bfloat16:
+        check(lib.vitk_th_mix_bwd_bf16(ptr(S), ptr(dPm), ptr(rmax), ptr(rsum), ptr(wl), ptr(bl), ptr(ww), ptr(bw), scale,
+                                       ptr(dS), ptr(dwl), ptr(dbl), ptr(dww), ptr(dbw), B, H, N, Np, _stream()),
+              "vitk_th_mix_bwd_bf16")
+        launch_count += 1
+        return dS
     check(lib.vitk_th_mix_bwd(ptr(S), ptr(dPm), ptr(rmax), ptr(rsum), ptr(wl), ptr(bl), ptr(ww), ptr(bw), scale, ptr(dS),
                               ptr(dwl), ptr(dbl), ptr(dww), ptr(dbw), B, H, N, Np, _stream()), "vitk_th_mix_bwd")
     launch_count += 1
