@@ -462,7 +462,8 @@ template <int H> static int th2_fwd_launch(const float* S, const float* wl, cons
     long long grid = (rows + TH2_WARPS - 1) / TH2_WARPS;
     const long long cap = (long long)sm_count() * 4;
     if (grid > cap) grid = cap;
-    th_mix2_fwd_kernel<H><<<(unsigned)grid, TH2_WARPS * 32, 0, st>>>(S, wl, bl, ww, bw, scale, Pm, rmax, rsum, B, N, Np);
+    if (Np <= 64) th_mix2_fwd_kernel<H, 4><<<(unsigned)grid, TH2_WARPS * 32, 0, st>>>(S, wl, bl, ww, bw, scale, Pm, rmax, rsum, B, N, Np);
+    else th_mix2_fwd_kernel<H, TH2_MAX_TILES><<<(unsigned)grid, TH2_WARPS * 32, 0, st>>>(S, wl, bl, ww, bw, scale, Pm, rmax, rsum, B, N, Np);
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
 }
 template <int H> static int th2_bwd_launch(const float* S, const __nv_bfloat16* dPm, const float* rmax, const float* rsum,
@@ -473,8 +474,12 @@ template <int H> static int th2_bwd_launch(const float* S, const __nv_bfloat16* 
     long long grid = (rows + TH2_WARPS - 1) / TH2_WARPS;
     const long long cap = (long long)sm_count() * 1;      // 1 block / SM (register budget); persistent over rows
     if (grid > cap) grid = cap;
-    th_mix2_bwd_kernel<H><<<(unsigned)grid, TH2_WARPS * 32, 0, st>>>(S, dPm, rmax, rsum, wl, bl, ww, scale, dS, dwl, dbl,
-                                                                    dww, dbw, B, N, Np);
+    if (Np <= 64)
+        th_mix2_bwd_kernel<H, 4><<<(unsigned)grid, TH2_WARPS * 32, 0, st>>>(S, dPm, rmax, rsum, wl, bl, ww, scale, dS, dwl,
+                                                                           dbl, dww, dbw, B, N, Np);
+    else
+        th_mix2_bwd_kernel<H, TH2_MAX_TILES><<<(unsigned)grid, TH2_WARPS * 32, 0, st>>>(S, dPm, rmax, rsum, wl, bl, ww, scale,
+                                                                                       dS, dwl, dbl, dww, dbw, B, N, Np);
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
 }
 

@@ -73,7 +73,7 @@ __device__ __forceinline__ void th2_c_to_a(const float (&c)[4], uint32_t (&a)[4]
 // ------------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------------
-template <int H>
+template <int H, int NT>
 __global__ void __launch_bounds__(TH2_WARPS * 32)
 th_mix2_fwd_kernel(const float* __restrict__ S, const float* __restrict__ wl, const float* __restrict__ bl,
                    const float* __restrict__ ww, const float* __restrict__ bw, float scale,
@@ -82,7 +82,6 @@ th_mix2_fwd_kernel(const float* __restrict__ S, const float* __restrict__ wl, co
     constexpr int KS = Th2<H>::KS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = lane >> 2, tig = lane & 3;
-    const int ntiles = (Np + 15) >> 4;
     const long long plane = (long long)N * Np;
     constexpr float kLog2e = 1.4426950408889634f;
 
@@ -113,27 +112,36 @@ th_mix2_fwd_kernel(const float* __restrict__ S, const float* __restrict__ wl, co
     for (long long row = (long long)blockIdx.x * TH2_WARPS + warp; row < rows; row += (long long)gridDim.x * TH2_WARPS) {
         const int b = static_cast<int>(row / N), i = static_cast<int>(row - (long long)b * N);
         const float* Srow = S + ((long long)b * H * N + i) * Np;
-        float sp[TH2_MAX_TILES][KS][4];   // mixed logits (log2 domain), C layout
+        // all loads of the row go out first (NT tiles x 2 x KS 8-byte loads per lane in flight): the row is one long
+        // dependent chain otherwise and the kernel would run at one HBM round trip per tile
+        float2 raw[NT][KS][2];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int col = t * 16 + 2 * gid;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const int h0 = 8 * ks + tig, h1 = h0 + 4;
+                raw[t][ks][0] = (col < Np && h0 < H) ? __ldg(reinterpret_cast<const float2*>(Srow + h0 * plane + col))
+                                                     : make_float2(0.f, 0.f);
+                raw[t][ks][1] = (col < Np && h1 < H) ? __ldg(reinterpret_cast<const float2*>(Srow + h1 * plane + col))
+                                                     : make_float2(0.f, 0.f);
+            }
+        }
+        float sp[NT][KS][4];   // mixed logits (log2 domain), C layout
         float mx[KS][2];
 #pragma unroll
         for (int nt = 0; nt < KS; ++nt) mx[nt][0] = mx[nt][1] = -INFINITY;
 #pragma unroll
-        for (int t = 0; t < TH2_MAX_TILES; ++t) {
-            if (t < ntiles) {
+        for (int t = 0; t < NT; ++t) {
+            {
                 const int col = t * 16 + 2 * gid;
-                const bool inb = col < Np;
                 uint32_t ah[KS][4], al[KS][4];
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
-                    const int h0 = 8 * ks + tig, h1 = h0 + 4;
-                    const float2 v0 = (inb && h0 < H) ? __ldg(reinterpret_cast<const float2*>(Srow + h0 * plane + col))
-                                                       : make_float2(0.f, 0.f);
-                    const float2 v1 = (inb && h1 < H) ? __ldg(reinterpret_cast<const float2*>(Srow + h1 * plane + col))
-                                                       : make_float2(0.f, 0.f);
-                    split_tf32(v0.x, ah[ks][0], al[ks][0]);
-                    split_tf32(v0.y, ah[ks][1], al[ks][1]);
-                    split_tf32(v1.x, ah[ks][2], al[ks][2]);
-                    split_tf32(v1.y, ah[ks][3], al[ks][3]);
+                    split_tf32(raw[t][ks][0].x, ah[ks][0], al[ks][0]);
+                    split_tf32(raw[t][ks][0].y, ah[ks][1], al[ks][1]);
+                    split_tf32(raw[t][ks][1].x, ah[ks][2], al[ks][2]);
+                    split_tf32(raw[t][ks][1].y, ah[ks][3], al[ks][3]);
                 }
 #pragma unroll
                 for (int nt = 0; nt < KS; ++nt) {
@@ -166,8 +174,8 @@ th_mix2_fwd_kernel(const float* __restrict__ S, const float* __restrict__ wl, co
                 sum[nt][e] = 0.f;
             }
 #pragma unroll
-        for (int t = 0; t < TH2_MAX_TILES; ++t) {
-            if (t < ntiles) {
+        for (int t = 0; t < NT; ++t) {
+            {
 #pragma unroll
                 for (int nt = 0; nt < KS; ++nt)
 #pragma unroll
@@ -196,8 +204,8 @@ th_mix2_fwd_kernel(const float* __restrict__ S, const float* __restrict__ wl, co
             }
         __nv_bfloat16* Prow = Pm + ((long long)b * H * N + i) * Np;
 #pragma unroll
-        for (int t = 0; t < TH2_MAX_TILES; ++t) {
-            if (t < ntiles) {
+        for (int t = 0; t < NT; ++t) {
+            {
                 const int col = t * 16 + 2 * gid;
                 uint32_t a[KS][4];
 #pragma unroll
@@ -234,7 +242,7 @@ template <int H> struct Th2Scratch {
     static constexpr int FLOATS = 4 * ARR;                        // dP' | dS' | P | S
 };
 
-template <int H>
+template <int H, int NT>
 __global__ void __launch_bounds__(TH2_WARPS * 32, 1)
 th_mix2_bwd_kernel(const float* __restrict__ S, const __nv_bfloat16* __restrict__ dPm, const float* __restrict__ rowmax,
                    const float* __restrict__ rowsum, const float* __restrict__ wl, const float* __restrict__ bl,
@@ -246,7 +254,6 @@ th_mix2_bwd_kernel(const float* __restrict__ S, const __nv_bfloat16* __restrict_
     __shared__ float red[2 * H * H + 2 * H];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = lane >> 2, tig = lane & 3;
-    const int ntiles = (Np + 15) >> 4;
     const long long plane = (long long)N * Np;
     constexpr float kLog2e = 1.4426950408889634f;
     float* sc_dpm = scratch_all[warp];
@@ -302,30 +309,40 @@ th_mix2_bwd_kernel(const float* __restrict__ S, const __nv_bfloat16* __restrict_
                 m2[nt][e] = g < H ? rowmax[((long long)b * H + g) * N + i] * kLog2e : 0.f;
                 inv[nt][e] = g < H ? 1.0f / rowsum[((long long)b * H + g) * N + i] : 0.f;
             }
-        float P[TH2_MAX_TILES][KS][4], dP[TH2_MAX_TILES][KS][4];
+        // all loads of the row first (see the forward kernel)
+        float2 rs[NT][KS][2];
+        uint32_t rd[NT][KS][2];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int col = t * 16 + 2 * gid;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const int h0 = 8 * ks + tig, h1 = h0 + 4;
+                const bool ok0 = col < Np && h0 < H, ok1 = col < Np && h1 < H;
+                rs[t][ks][0] = ok0 ? __ldg(reinterpret_cast<const float2*>(S + base + h0 * plane + col)) : make_float2(0.f, 0.f);
+                rs[t][ks][1] = ok1 ? __ldg(reinterpret_cast<const float2*>(S + base + h1 * plane + col)) : make_float2(0.f, 0.f);
+                rd[t][ks][0] = ok0 ? __ldg(reinterpret_cast<const uint32_t*>(dPm + base + h0 * plane + col)) : 0u;
+                rd[t][ks][1] = ok1 ? __ldg(reinterpret_cast<const uint32_t*>(dPm + base + h1 * plane + col)) : 0u;
+            }
+        }
+        float P[NT][KS][4], dP[NT][KS][4];
         float rp[KS][2];
 #pragma unroll
         for (int nt = 0; nt < KS; ++nt) rp[nt][0] = rp[nt][1] = 0.f;
         // ---- phase 1: P, dP and rowsum(dP o P)
 #pragma unroll
-        for (int t = 0; t < TH2_MAX_TILES; ++t) {
-            if (t < ntiles) {
+        for (int t = 0; t < NT; ++t) {
+            {
                 const int col = t * 16 + 2 * gid;
-                const bool inb = col < Np;
                 uint32_t ah[KS][4], al[KS][4], ad[KS][4];
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
-                    const int h0 = 8 * ks + tig, h1 = h0 + 4;
-                    const float2 v0 = (inb && h0 < H) ? __ldg(reinterpret_cast<const float2*>(S + base + h0 * plane + col))
-                                                       : make_float2(0.f, 0.f);
-                    const float2 v1 = (inb && h1 < H) ? __ldg(reinterpret_cast<const float2*>(S + base + h1 * plane + col))
-                                                       : make_float2(0.f, 0.f);
+                    const float2 v0 = rs[t][ks][0], v1 = rs[t][ks][1];
                     split_tf32(v0.x, ah[ks][0], al[ks][0]);
                     split_tf32(v0.y, ah[ks][1], al[ks][1]);
                     split_tf32(v1.x, ah[ks][2], al[ks][2]);
                     split_tf32(v1.y, ah[ks][3], al[ks][3]);
-                    const uint32_t d0 = (inb && h0 < H) ? __ldg(reinterpret_cast<const uint32_t*>(dPm + base + h0 * plane + col)) : 0u;
-                    const uint32_t d1 = (inb && h1 < H) ? __ldg(reinterpret_cast<const uint32_t*>(dPm + base + h1 * plane + col)) : 0u;
+                    const uint32_t d0 = rd[t][ks][0], d1 = rd[t][ks][1];
                     // bf16 -> fp32 bit patterns (exactly representable in tf32); the pad columns [N, Np) of the buffers
                     // are never written by the producing GEMM and may hold anything: zero them
                     ad[ks][0] = col < N ? (d0 << 16) : 0u;
@@ -367,8 +384,8 @@ th_mix2_bwd_kernel(const float* __restrict__ S, const __nv_bfloat16* __restrict_
             }
         // ---- phase 2: dS', dS, weight gradients
 #pragma unroll
-        for (int t = 0; t < TH2_MAX_TILES; ++t) {
-            if (t < ntiles) {
+        for (int t = 0; t < NT; ++t) {
+            {
                 const int col = t * 16 + 2 * gid;
                 const bool inb = col < Np;
                 float dsp[KS][4];
@@ -399,13 +416,9 @@ th_mix2_bwd_kernel(const float* __restrict__ S, const __nv_bfloat16* __restrict_
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
                     const int h0 = 8 * ks + tig, h1 = h0 + 4;
-                    // S and dP' are re-read from memory in A layout (L1 / L2 hits: this row was read in phase 1)
-                    const float2 s0 = (inb && h0 < H) ? __ldg(reinterpret_cast<const float2*>(S + base + h0 * plane + col))
-                                                       : make_float2(0.f, 0.f);
-                    const float2 s1 = (inb && h1 < H) ? __ldg(reinterpret_cast<const float2*>(S + base + h1 * plane + col))
-                                                       : make_float2(0.f, 0.f);
-                    const uint32_t d0 = (inb && h0 < H) ? __ldg(reinterpret_cast<const uint32_t*>(dPm + base + h0 * plane + col)) : 0u;
-                    const uint32_t d1 = (inb && h1 < H) ? __ldg(reinterpret_cast<const uint32_t*>(dPm + base + h1 * plane + col)) : 0u;
+                    // S and dP' in A layout: still in the registers the row was loaded into
+                    const float2 s0 = rs[t][ks][0], s1 = rs[t][ks][1];
+                    const uint32_t d0 = rd[t][ks][0], d1 = rd[t][ks][1];
                     const float2 e0 = make_float2(col < N ? bf16_lo(d0) : 0.f, col + 1 < N ? bf16_hi(d0) : 0.f);
                     const float2 e1 = make_float2(col < N ? bf16_lo(d1) : 0.f, col + 1 < N ? bf16_hi(d1) : 0.f);
                     const float2 t0 = make_float2(col < N ? s0.x : 0.f, col + 1 < N ? s0.y : 0.f);
