@@ -225,6 +225,17 @@ int vitk_attn_bwd_ex(const void* qkv_bf16, const void* out_bf16, const void* dou
                      void* dqkv_bf16, float* dqkv_bias_grad, int B, int N, int H, int d, float scale, void* stream);
 
 /*
+ * Whole-head attention backward for short sequences (d = 64, N <= 256: every ViT-S/B 16 / DeiT configuration at 224 px):
+ * one thread block per (image, head) stages Q, K, V, dO of the head once, computes S and dP ONCE per tile pair, keeps
+ * dQ (4 query tiles), dK and dV in TMEM and forms delta in its prologue -- no atomics, no workspace, no second kernel.
+ * Same inputs / outputs / determinism as vitk_attn_bwd_ex. vitk_attn_bwd_head_supported(N, d) tells the caller whether it
+ * applies (VITK_ATTN_BWD_HEAD=0 turns it off for A/B runs).
+ */
+int vitk_attn_bwd_head_supported(int N, int d);
+int vitk_attn_bwd_head(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2,
+                       void* dqkv_bf16, float* dqkv_bias_grad, int B, int N, int H, int d, float scale, void* stream);
+
+/*
  * Single-kernel attention backward (d = 64): S / dP and the elementwise pass are computed once per (key block, query
  * tile); dV, dK accumulate in TMEM, dQ tiles are summed across key blocks with fp32 atomics into the caller-provided
  * workspace dq_f32_ws [B*N, H*d] (zeroed inside) and then written as bf16 into dqkv. Launches: delta pre-pass, memset,

@@ -42,15 +42,19 @@ def test_attn_fwd(B, N, H, d, variant, monkeypatch):
     assert e_l <= 1e-3
 
 
-@pytest.mark.parametrize("variant", ["two_kernel_wg2", "two_kernel_wg1", "fused"])
-@pytest.mark.parametrize("B,N,H,d", CASES)
+@pytest.mark.parametrize("variant", ["head", "two_kernel_wg2", "two_kernel_wg1", "fused"])
+@pytest.mark.parametrize("B,N,H,d", CASES + [(40, 197, 12, 64), (3, 129, 2, 64), (2, 64, 2, 64), (2, 200, 1, 64)])
 def test_attn_bwd(B, N, H, d, variant, monkeypatch):
-    """two_kernel_wg2: the two deterministic kernels with eight elementwise warps per CTA (default); two_kernel_wg1:
-    the four-warp kernels (VITK_ATTN_WG2=0); fused: the single-kernel backward (d = 64 only)."""
-    from vit_torch_b200 import ops
+    """head: one block per (image, head) computes dQ, dK, dV in a single pass (default for N <= 256, d = 64);
+    two_kernel_wg2: the two deterministic kernels with eight elementwise warps per CTA (default otherwise);
+    two_kernel_wg1: the four-warp kernels (VITK_ATTN_WG2=0); fused: the single-kernel backward with fp32 dQ atomics."""
+    from vit_torch_b200 import _lib, ops
     fused = variant == "fused"
     if fused and d != 64:
         pytest.skip("single-kernel backward is d = 64 only")
+    monkeypatch.setenv("VITK_ATTN_BWD_HEAD", "1" if variant == "head" else "0")
+    if variant == "head" and not _lib.load().vitk_attn_bwd_head_supported(N, d):
+        pytest.skip("whole-head backward serves N <= 256, d = 64")
     monkeypatch.setenv("VITK_ATTN_WG2", "0" if variant == "two_kernel_wg1" else "1")
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + N + 7)
     qkv = (torch.randn((B * N, 3 * H * d), device="cuda", generator=g) * 1.2).to(torch.bfloat16)

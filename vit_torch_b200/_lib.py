@@ -57,6 +57,8 @@ SIGNATURES = {
     "vitk_class_attn_bwd": [_P, _P, _P, _P, _P, _L, _L, _P, _P, _F, _P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _I, _P],
     "vitk_attn_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "vitk_attn_bwd_ex": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "vitk_attn_bwd_head_supported": [_I, _I],
+    "vitk_attn_bwd_head": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "vitk_attn_bwd_fused": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
 }
 

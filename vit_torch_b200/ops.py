@@ -185,8 +185,14 @@ def attn_bwd(qkv, out, dout, lse2, B, N, H, d, scale, fused=None, dbias=None):
     _need_cuda(qkv, out, dout, lse2)
     assert dout.dtype == torch.bfloat16 and dout.is_contiguous() and out.is_contiguous() and qkv.is_contiguous()
     dqkv = torch.empty_like(qkv)
-    delta = torch.empty_like(lse2)
     lib = _lib.load()
+    if not fused and lib.vitk_attn_bwd_head_supported(N, d):
+        # short sequences: one block per (image, head) produces dQ, dK, dV in a single pass
+        check(lib.vitk_attn_bwd_head(ptr(qkv), ptr(out), ptr(dout), ptr(lse2), ptr(dqkv), ptr(dbias), B, N, H, d, scale,
+                                     _stream()), "vitk_attn_bwd_head")
+        launch_count += 1
+        return dqkv
+    delta = torch.empty_like(lse2)
     if d == 64 and N <= 8192 and (_ATTN_BWD_FUSED if fused is None else fused):
         # single-kernel backward; dQ tiles of different key blocks meet in an fp32 workspace (zeroed by the library)
         dq32 = torch.empty((B * N, H * d), dtype=torch.float32, device=qkv.device)
