@@ -228,8 +228,9 @@ int vitk_attn_bwd_ex(const void* qkv_bf16, const void* out_bf16, const void* dou
  * Whole-head attention backward for short sequences (d = 64, N <= 256: every ViT-S/B 16 / DeiT configuration at 224 px):
  * one thread block per (image, head) stages Q, K, V, dO of the head once, computes S and dP ONCE per tile pair, keeps
  * dQ (4 query tiles), dK and dV in TMEM and forms delta in its prologue -- no atomics, no workspace, no second kernel.
- * Same inputs / outputs / determinism as vitk_attn_bwd_ex. vitk_attn_bwd_head_supported(N, d) tells the caller whether it
- * applies (VITK_ATTN_BWD_HEAD=0 turns it off for A/B runs).
+ * Same inputs / outputs / determinism as vitk_attn_bwd_ex. Opt-in: vitk_attn_bwd_head_supported(N, d) returns 1 only
+ * with VITK_ATTN_BWD_HEAD=1 in the environment (measured slower than the two-kernel backward at 197 tokens: one block
+ * per SM leaves one tile chain in flight instead of two; kept parity-tested).
  */
 int vitk_attn_bwd_head_supported(int N, int d);
 int vitk_attn_bwd_head(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2,

@@ -35,7 +35,7 @@ for name, B, N, H, d in (("vitb16_bs128", 128, 197, 12, 64), ("vitb8_bs64", 64, 
             continue
         r[f"bwd_{variant}_us"] = timeit(lambda: ops.attn_bwd(qkv, out, dout, lse2, B, N, H, d, scale, dbias=dbias))
         r[f"bwd_{variant}_tflops"] = 2.5 * fl / r[f"bwd_{variant}_us"] / 1e6
-    os.environ.pop("VITK_ATTN_BWD_HEAD", None)
+    os.environ.pop("VITK_ATTN_BWD_HEAD", None)     # default: two-kernel
     print(r, flush=True)
     rows.append(r)
 path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/bench_attn.json"

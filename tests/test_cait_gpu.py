@@ -126,10 +126,8 @@ def test_cait_matches_oracle(name, B):
             continue
         ge = nerr(p.grad, r)
         worst = max(worst, (ge, k))
-        # The H x H talking-heads mixing parameters (<= 272 elements) are global sums over B*H*N*N terms of mixed
-        # sign: bf16 rounding of dO / V does not average out relative to the (cancelled) total at batch 2, so they
-        # get 4e-2; every other tensor must meet the 2e-2 north-star tolerance. Direction (cosine) is checked for all.
-        tol = 4e-2 if (".proj_l." in k or ".proj_w." in k) else TOL
-        assert ge <= tol, f"{k}: {ge:.3e}"
+        # every tensor, the H x H talking-heads mixing parameters included, meets the 2e-2 north-star tolerance
+        # (measured on B200: worst 1.9e-2 on blocks.3.attn.proj_w.bias, 1.8e-2 on a proj_l.weight)
+        assert ge <= TOL, f"{k}: {ge:.3e}"
         assert cosine(p.grad, r) >= 0.999, k
     print("worst grad", worst)

@@ -58,7 +58,7 @@ def _compare(ours, ref, x, labels, tol=2e-2, tol_grad=2e-2):
 
 
 @pytest.mark.parametrize("arch,B,size", [("dino_vits16", 4, 224), ("dino_vits16", 3, 96), ("dino_vits8", 2, 96),
-                                         ("dino_vitb16", 2, 224)])
+                                         ("dino_vitb16", 2, 224), ("dino_vitb8", 2, 224)])   # last: BASELINE config 3, N = 785
 def test_dino_matches_oracle(arch, B, size):
     from oracle import vit as ovit
     from vit_torch_b200 import models

@@ -42,7 +42,7 @@ def test_loss_curve_overlays_oracle_200_steps():
     print(f"loss start {lr[0]:.4f}/{lo[0]:.4f} end {sr[-1]:.4f}/{so[-1]:.4f}; max smoothed rel diff {rel:.3e}")
     assert sr[-1] < 0.8 * sr[0], "oracle loss did not fall: the test data is not learnable"
     assert abs(lo[0] - lr[0]) <= 2e-2 * abs(lr[0])
-    assert rel <= 5e-2, "bf16 loss curve departs from the fp32 oracle"
+    assert rel <= 2e-2, "bf16 loss curve departs from the fp32 oracle"      # measured on B200: 3.5e-3
 
 
 def test_lineareval_flow():

@@ -350,9 +350,13 @@ int make_tok_tmap2d(CUtensorMap* out, const void* p, long long rows, long long c
 
 using namespace vitk;
 
+// Opt-in (VITK_ATTN_BWD_HEAD=1): measured on B200, ViT-B/16 bs128: 281 us vs 222 us for the two-kernel backward. With
+// 512 TMEM columns the block is alone on its SM and its per-tile chain (S^T MMA -> exp / dS -> dV / dK / dQ MMAs) is
+// latency-bound, so the SM works on ONE tile at a time where two co-resident blocks of the two-kernel form overlap two;
+// the saved recompute does not make up for that. Kept parity-tested for the next step (two tiles in flight per block).
 extern "C" int vitk_attn_bwd_head_supported(int N, int d) {
     const char* e = getenv("VITK_ATTN_BWD_HEAD");
-    if (e != nullptr && e[0] == '0') return 0;
+    if (e == nullptr || e[0] != '1') return 0;
     return (d == 64 && N >= 1 && N <= ABH_MAX_N) ? 1 : 0;
 }
 

@@ -187,7 +187,7 @@ def attn_bwd(qkv, out, dout, lse2, B, N, H, d, scale, fused=None, dbias=None):
     dqkv = torch.empty_like(qkv)
     lib = _lib.load()
     if not fused and lib.vitk_attn_bwd_head_supported(N, d):
-        # short sequences: one block per (image, head) produces dQ, dK, dV in a single pass
+        # opt-in (VITK_ATTN_BWD_HEAD=1): one block per (image, head) produces dQ, dK, dV in a single pass
         check(lib.vitk_attn_bwd_head(ptr(qkv), ptr(out), ptr(dout), ptr(lse2), ptr(dqkv), ptr(dbias), B, N, H, d, scale,
                                      _stream()), "vitk_attn_bwd_head")
         launch_count += 1
