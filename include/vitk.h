@@ -129,6 +129,14 @@ int vitk_colsum_prod(const float* a, long long lda, const void* b_bf16, long lon
 int vitk_colsum_prod_ex(const float* a, long long lda, const void* b_bf16, long long ldb, long long rows, int N,
                         float* out, const float* rowscale, long long rows_per_sample, void* stream);
 
+/* LayerScale branch backward in one pass (models/cait.py:144-149, y = x + gamma * DropPath(f)):
+ *   out_bf16[r,c] = bf16(dy[r,c] * gamma[c] * rowscale[r / rows_per_sample])   (gradient of f: operand of the dgrad / wgrad)
+ *   dgamma[c] += sum_r dy * rowscale * f ;  dbias[c] += sum_r dy * gamma * rowscale   (bias gradient of f's Linear)
+ * rowscale / dgamma / dbias may be null. out_bf16 is dense [rows, N]. N % 8 == 0. */
+int vitk_layerscale_bwd(const float* dy, long long lddy, const void* f_bf16, long long ldf, const float* gamma,
+                        const float* rowscale, long long rows_per_sample, long long rows, int N, void* out_bf16,
+                        float* dgamma, float* dbias, void* stream);
+
 /* out_bf16[r,:] = bf16(x[(r / rows_per_group) * group_stride + (r % rows_per_group) * D + :] * colscale * rowscale[r / rows_per_sample])
  * -- the bf16 copy of a residual-stream gradient that the dgrad/wgrad GEMMs read (LayerScale / DropPath folded in),
  * also used to compact dX[:, T:, :] into patch rows for the PatchEmbed wgrad. D % 8 == 0. */

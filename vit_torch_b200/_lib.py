@@ -35,6 +35,7 @@ SIGNATURES = {
     "vitk_cross_entropy": [_P, _L, _P, _I, _I, _P, _P, _L, _P],
     "vitk_colsum_prod": [_P, _L, _P, _L, _L, _I, _P, _P],
     "vitk_colsum_prod_ex": [_P, _L, _P, _L, _L, _I, _P, _P, _L, _P],
+    "vitk_layerscale_bwd": [_P, _L, _P, _L, _P, _P, _L, _L, _I, _P, _P, _P, _P],
     "vitk_scale_cast": [_P, _L, _L, _L, _I, _P, _P, _L, _P, _P],
     "vitk_patchify": [_P, _P, _I, _I, _I, _I, _I, _P],
     "vitk_patch_embed_fwd": [_P, _I, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],

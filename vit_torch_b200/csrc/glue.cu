@@ -586,6 +586,63 @@ colsum_prod_kernel(const float* __restrict__ a, long long lda, const __nv_bfloat
 }
 
 // ------------------------------------------------------------------------------------------------
+// LayerScale branch backward in ONE pass (models/cait.py:144-149: x + gamma * DropPath(f)):
+//   out_bf16[r, c] = bf16(dy[r, c] * gamma[c] * rs[r])     the gradient of the branch output f, A operand of the
+//                                                           proj / fc2 dgrad and wgrad GEMMs
+//   dgamma[c]  += sum_r dy[r, c] * rs[r] * f[r, c]
+//   dbias[c]   += sum_r dy[r, c] * gamma[c] * rs[r]         the bias gradient of the Linear that produced f
+// (replaces colsum_prod + scale_cast + colsum_bf16: three passes over [rows, D] per branch)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+layerscale_bwd_kernel(const float* __restrict__ dy, long long lddy, const __nv_bfloat16* __restrict__ f, long long ldf,
+                      const float* __restrict__ gamma, const float* __restrict__ rowscale, long long rps, long long rows,
+                      int N, __nv_bfloat16* __restrict__ out, float* __restrict__ dgamma, float* __restrict__ dbias) {
+    __shared__ float red[8][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = blockIdx.x * 256 + lane * 8;
+    float ag[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ab[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (col + 8 <= N) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        for (long long r = (long long)blockIdx.y * 8 + warp; r < rows; r += (long long)gridDim.y * 8) {
+            const uint4 v = ld_nc_v4(f + r * ldf + col);
+            const float4 a0 = *reinterpret_cast<const float4*>(dy + r * lddy + col);
+            const float4 a1 = *reinterpret_cast<const float4*>(dy + r * lddy + col + 4);
+            const float rs = rowscale != nullptr ? __ldg(rowscale + r / rps) : 1.0f;
+            const float a[8] = {a0.x * rs, a0.y * rs, a0.z * rs, a0.w * rs, a1.x * rs, a1.y * rs, a1.z * rs, a1.w * rs};
+            const float fv[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
+                                 bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                ag[j] = fmaf(a[j], fv[j], ag[j]);
+                o[j] = a[j] * gm[j];
+                ab[j] += o[j];
+            }
+            st_v4(out + r * N + col, make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
+                                                pack_bf16(o[6], o[7])));
+        }
+    }
+    const int c = blockIdx.x * 256 + threadIdx.x;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        float* dst = pass == 0 ? dgamma : dbias;
+        if (dst == nullptr) continue;       // (uniform)
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? ag[j] : ab[j];
+        __syncthreads();
+        if (c < N) {
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sum += red[k][threadIdx.x];
+            atomicAdd(dst + c, sum);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // fp32 -> bf16 with optional per-column / per-sample scale and token-row compaction:
 //   out[r, :] = bf16(x[(r / rpg) * group_stride + (r % rpg) * D + :] * colscale[:] * rowscale[r / rps])
 // (bf16 copy of the residual gradient the dgrad/wgrad GEMMs consume; dX[:, T:, :] -> patch rows for PatchEmbed wgrad)
@@ -959,6 +1016,24 @@ extern "C" int vitk_colsum_prod_ex(const float* a, long long lda, const void* b_
     if (gy < 1) gy = 1;
     colsum_prod_kernel<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(a, lda, reinterpret_cast<const __nv_bfloat16*>(b_bf16), ldb,
                                                               rows, N, out, rowscale, rows_per_sample);
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
+extern "C" int vitk_layerscale_bwd(const float* dy, long long lddy, const void* f_bf16, long long ldf, const float* gamma,
+                                   const float* rowscale, long long rows_per_sample, long long rows, int N,
+                                   void* out_bf16, float* dgamma, float* dbias, void* stream) {
+    if (rows <= 0 || N <= 0 || (N % 8) != 0 || (lddy % 4) != 0 || (ldf % 8) != 0 || !dy || !f_bf16 || !gamma || !out_bf16 ||
+        (rowscale != nullptr && rows_per_sample <= 0))
+        return VITK_ERR_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int gx = (N + 255) / 256;
+    long long gy = (4LL * sm_count() + gx - 1) / gx;
+    const long long max_gy = (rows + 7) / 8;
+    if (gy > max_gy) gy = max_gy;
+    if (gy < 1) gy = 1;
+    layerscale_bwd_kernel<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(dy, lddy, reinterpret_cast<const __nv_bfloat16*>(f_bf16),
+                                                                 ldf, gamma, rowscale, rows_per_sample, rows, N,
+                                                                 reinterpret_cast<__nv_bfloat16*>(out_bf16), dgamma, dbias);
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
 }
 

@@ -194,15 +194,19 @@ class BlockFn(torch.autograd.Function):
             dx2._vitk_colsum = getattr(dout, "_vitk_colsum", None)
 
         # ---- Mlp branch: x2 = x1 + g2 * rowscale * (fc2(gelu(fc1(h2))))
-        if dg2 is not None:
-            ops.colsum_prod_accum(dx2, f2, dg2, rowscale=rs2, rows_per_sample=N)   # d_gamma = sum dY * rowscale * f
-        dx2b = _dy_bf16(dx2, M, D, g2, rs2, N)
+        fc2b_done = False
+        if g2 is not None and f2 is not None:
+            # LayerScale: bf16(dY * gamma * rowscale), d_gamma = sum dY * rowscale * f and the fc2 bias gradient in ONE pass
+            dx2b = ops.layerscale_bwd(dx2, f2, g2, rs2, N, dgamma=dg2, dbias=dfc2b)
+            fc2b_done = True
+        else:
+            dx2b = _dy_bf16(dx2, M, D, g2, rs2, N)
         da = torch.empty((M, hidden), dtype=torch.bfloat16, device=dev)
         # fc2 dgrad with GELU' fused; the same epilogue reduces da over rows = fc1 bias gradient
         ops.gemm(dx2b, wfc2, b_mn=True, epilogue=ops.EPI_DGELU, aux=a, out=da, colsum=dfc1b)
         if dfc2w is not None:
             ops.gemm(dx2b, g, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dfc2w)
-        if dfc2b is not None:
+        if dfc2b is not None and not fc2b_done:
             side = getattr(dx2, "_vitk_colsum", None) if dx2b is getattr(dx2, "_vitk_bf16", None) else None
             if side is not None:
                 dfc2b.add_(side)        # column sums of dx2b were produced by the kernel that wrote dx2b
@@ -217,16 +221,18 @@ class BlockFn(torch.autograd.Function):
         plain1 = g1 is None and rs1 is None
         dx1, dx1b = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dx2, dweight=dn2w, dbias=dn2b, want_bf16=plain1,
                                       dxsum=dprojb if plain1 else None)
-        if dg1 is not None:
-            ops.colsum_prod_accum(dx1, f1, dg1, rowscale=rs1, rows_per_sample=N)
-        if not plain1:
+        projb_done = plain1
+        if g1 is not None and f1 is not None:
+            dx1b = ops.layerscale_bwd(dx1, f1, g1, rs1, N, dgamma=dg1, dbias=dprojb)
+            projb_done = True
+        elif not plain1:
             dx1b = ops.scale_cast(dx1, M, D, colscale=g1, rowscale=rs1, rows_per_sample=N)
         # ---- attention branch
         do = dh2  # reuse the buffer: dO [M, D] bf16
         ops.gemm(dx1b, wproj, b_mn=True, epilogue=ops.EPI_STORE_BF16, out=do)
         if dprojw is not None:
             ops.gemm(dx1b, o, a_mn=True, b_mn=True, epilogue=ops.EPI_ATOMIC_F32, out=dprojw)
-        if dprojb is not None and not plain1:
+        if dprojb is not None and not projb_done:
             ops.colsum_accum(dx1b, dprojb)
         attn_dbias_done = False
         if thl_w is None:

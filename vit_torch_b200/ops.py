@@ -276,6 +276,20 @@ def colsum_prod_accum(a, b, out, rowscale=None, rows_per_sample=1):
     launch_count += 1
 
 
+def layerscale_bwd(dy, f, gamma, rowscale=None, rows_per_sample=1, dgamma=None, dbias=None):
+    """One pass over a LayerScale branch's gradient: returns bf16(dy * gamma * rowscale) [rows, D]; dgamma += sum dy *
+    rowscale * f; dbias += column sums of the returned matrix (see vitk_layerscale_bwd)."""
+    global launch_count
+    _need_cuda(dy, f, gamma)
+    assert dy.dtype == torch.float32 and f.dtype == torch.bfloat16 and dy.shape == f.shape
+    rows, D = dy.shape
+    out = torch.empty((rows, D), dtype=torch.bfloat16, device=dy.device)
+    check(_lib.load().vitk_layerscale_bwd(ptr(dy), _ld(dy), ptr(f), _ld(f), ptr(gamma), ptr(rowscale), rows_per_sample, rows,
+                                          D, ptr(out), ptr(dgamma), ptr(dbias), _stream()), "vitk_layerscale_bwd")
+    launch_count += 1
+    return out
+
+
 def scale_cast(x, rows, D, *, rows_per_group=None, group_stride=0, colscale=None, rowscale=None, rows_per_sample=0,
                offset_elems=0):
     """bf16 [rows, D] = x (fp32) * colscale * rowscale with optional token-row compaction (see vitk_scale_cast)."""
@@ -475,7 +489,7 @@ def _timed(fn):
 
 
 for _name in ("gemm", "gemm_batched", "layernorm_fwd", "layernorm_bwd", "layernorm_fwd_rows", "layernorm_bwd_rows",
-              "colsum_accum", "colsum_f32_accum", "colsum_prod_accum", "cast_bf16", "attn_fwd", "attn_bwd", "scale_cast",
+              "colsum_accum", "colsum_f32_accum", "colsum_prod_accum", "layerscale_bwd", "cast_bf16", "attn_fwd", "attn_bwd", "scale_cast",
               "patchify", "prefix_tokens", "patch_embed_fwd", "patch_embed_wgrad", "normalize_u8", "th_mix_fwd", "th_mix_bwd", "class_attn_fwd", "class_attn_bwd"):
     globals()[_name] = _timed(globals()[_name])
 
