@@ -389,9 +389,11 @@ def main():
     ap.add_argument("--e2e-sync-read", action="store_true",
                     help="e2e: read each step's loss with a blocking .item() right after enqueueing it (A/B; default: "
                          "the read of step i happens after step i+1 has been enqueued)")
-    ap.add_argument("--dp", default="auto", choices=["auto", "deferred", "overlap", "bf16"],
+    ap.add_argument("--dp", default="auto", choices=["auto", "deferred", "overlap", "bf16", "split"],
                     help="DP gradient exchange: deferred = one fp32 all-reduce over the gradient arena after backward; "
-                         "bf16 = the same in bf16; overlap = per-block all-reduces overlapped with backward")
+                         "bf16 = the same in bf16; split = backward captured as two graphs, the first half's all-reduce "
+                         "runs on --nccl-ctas thread blocks under the second graph; overlap = per-block all-reduces "
+                         "overlapped with an eagerly launched backward")
     ap.add_argument("--overlap", action="store_true", help="(= --dp overlap)")
     ap.add_argument("--no-overlap", action="store_true", help="(default behaviour; kept for older command lines)")
     ap.add_argument("--nccl-ctas", type=int, default=4,
@@ -417,7 +419,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dp_mode = "none" if world == 1 else ("bf16" if args.dp == "auto" else args.dp)
+    dp_mode = "none" if world == 1 else ("split" if args.dp == "auto" else args.dp)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         from vit_torch_b200.dist import configure_sm_partition
@@ -433,7 +435,8 @@ def main():
             dist.broadcast(p.data, 0)
     reducer = None
     if world > 1:
-        reducer = GradAllReducer(model, overlap=(dp_mode == "overlap"), compress=(dp_mode == "bf16"))
+        reducer = GradAllReducer(model, overlap=(dp_mode == "overlap"), compress=(dp_mode == "bf16"),
+                                 split=(dp_mode == "split"), split_ctas=args.nccl_ctas)
     trainer = train.Trainer(model, lr=1e-3, momentum=0.9, reducer=reducer, graph=(not args.no_graph), strict_graph=True)
 
     x_host, y_host = synth_batch(bs, w["size"], 1000 + rank, args.input)
@@ -636,7 +639,11 @@ def main():
                                           "overlap": f"per-block NCCL all-reduces overlapped with backward, NCCL_MAX_CTAS={args.nccl_ctas}",
                                           "deferred": "one NCCL all-reduce over the fp32 gradient arena after backward",
                                           "bf16": "gradient arena cast to bf16 by one kernel, one NCCL all-reduce (bf16, "
-                                                  "average), optimiser reads the bf16 gradients"}[dp_mode]},
+                                                  "average), cast back into the fp32 arena",
+                                          "split": "backward replayed as two CUDA graphs; the fp32 gradients of the last "
+                                                   "two thirds of the blocks are all-reduced on a side stream by a "
+                                                   f"communicator capped at {args.nccl_ctas} thread blocks while the second "
+                                                   "graph runs; the remaining third is reduced after it"}[dp_mode]},
             "step_tflops_per_gpu": step_fl / (ms / args.steps * 1e-3) / 1e12,
             "step_frac_of_bf16_peak": step_fl / (ms / args.steps * 1e-3) / 1e12 / pk["bf16_sustained"],
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,

@@ -29,11 +29,13 @@ def main():
         return m
 
     m = make()
-    red = GradAllReducer(m, overlap=(mode == "overlap"), compress=(mode == "bf16"))
+    red = GradAllReducer(m, overlap=(mode == "overlap"), compress=(mode == "bf16"), split=(mode == "split"))
     tr = train.Trainer(m, lr=0.0, momentum=0.0, reducer=red, graph=(mode != "overlap"), strict_graph=True)
     x, y = X[rank * bs:(rank + 1) * bs].to(dev), Y[rank * bs:(rank + 1) * bs].to(dev)
     for _ in range(4):                       # 2 eager steps, the capture step, one replay (lr 0: weights unchanged)
         tr.step(x, y)
+    if mode == "split":
+        assert tr._graph2 is not None and 0 < tr._split_off < tr.arena.off, "backward was not split into two graphs"
     torch.cuda.synchronize()
     got = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
     red.close()

@@ -12,11 +12,11 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("mode", ["deferred", "overlap", "bf16"])
+@pytest.mark.parametrize("mode", ["deferred", "overlap", "bf16", "split"])
 def test_nccl_gradients_match_single_gpu(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    port = 29600 + {"deferred": 1, "overlap": 2, "bf16": 3}[mode]
+    port = 29600 + {"deferred": 1, "overlap": 2, "bf16": 3, "split": 4}[mode]
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
                         os.path.join(HERE, "dist_parity_worker.py"), mode], capture_output=True, text=True, timeout=900)

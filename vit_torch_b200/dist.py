@@ -41,11 +41,30 @@ def configure_sm_partition(nccl_ctas: int = 4) -> None:
     _partition_limit = max(n - int(os.environ["NCCL_MAX_CTAS"]), n // 2)
 
 
+def partition_limit(nccl_ctas: int) -> int:
+    """SMs left to the persistent kernels while a collective capped at nccl_ctas thread blocks shares the GPU."""
+    n = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return max(n - int(nccl_ctas), n // 2)
+
+
 class GradAllReducer:
-    def __init__(self, model: torch.nn.Module, process_group=None, overlap: bool = True, compress: bool = False):
+    def __init__(self, model: torch.nn.Module, process_group=None, overlap: bool = True, compress: bool = False,
+                 split: bool = False, split_ctas: int = 4):
         self.model = model
         self.compress = bool(compress) and not overlap     # deferred mode only: bf16 gradients on the wire
         self._wire = None
+        # split mode (graph Trainer): backward is captured as two graphs; the gradients of the first half (the last
+        # blocks) are all-reduced on a side stream by a communicator capped at `split_ctas` thread blocks WHILE the second
+        # graph runs on the other SMs; only the second half's all-reduce is exposed.
+        self.split = bool(split) and not overlap
+        self.split_ctas = int(split_ctas)
+        self.pg_side = None
+        self._side_done = None
+        if self.split and dist.is_initialized() and dist.get_world_size(process_group) > 1 \
+                and next(model.parameters()).is_cuda:
+            self.world = dist.get_world_size(process_group)
+            self.cuda = True
+            self.side_group()           # collective call: every rank constructs its reducer
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.overlap = overlap
@@ -86,6 +105,40 @@ class GradAllReducer:
     def discard_pending(self):
         """Forget bucket notifications (used after a CUDA-graph capture of backward: replays fire no hooks)."""
         self._pending.clear()
+
+    def side_group(self):
+        """Communicator for the overlapped half: NCCL thread blocks capped (they share the GPU with the second graph)."""
+        if self.pg_side is None and self.world > 1 and self.cuda:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = self.split_ctas
+            opts.config.min_ctas = min(self.split_ctas, 1) or 1
+            self.pg_side = dist.new_group(ranks=list(range(self.world)), pg_options=opts)
+        return self.pg_side
+
+    def reduce_first_half(self, arena, end: int) -> None:
+        """Enqueue the all-reduce of arena[0:end] on the communication stream, ordered after everything enqueued so far
+        on the current stream. Returns immediately; reduce_second_half() joins it."""
+        if self.world <= 1 or end <= 0:
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            dist.all_reduce(arena.buf[:end], op=dist.ReduceOp.AVG, group=self.side_group())
+            self._side_done = torch.cuda.Event()
+            self._side_done.record(self.comm_stream)
+        self.collectives += 1
+
+    def reduce_second_half(self, arena, start: int) -> None:
+        """All-reduce arena[start:used] on the current stream (all SMs), then join the first half."""
+        if self.world <= 1:
+            return
+        if arena.off > start:
+            dist.all_reduce(arena.buf[start:arena.off], op=dist.ReduceOp.AVG, group=self.pg)
+            self.collectives += 1
+        if self._side_done is not None:
+            torch.cuda.current_stream().wait_event(self._side_done)
+            self._side_done = None
 
     def _reduce_arena(self, arena):
         """ONE collective over the used part of the gradient arena (average). compress: the arena is cast to bf16 by one

@@ -283,6 +283,11 @@ class Trainer:
         # NCCL calls from inside backward and stays eager.
         self.use_graph = bool(graph) and (reducer is None or not getattr(reducer, "overlap", True))
         self.opt_in_graph = reducer is None
+        # split mode (dist.GradAllReducer(split=True)): backward captured as two graphs around block `split_at`
+        self.split = self.use_graph and reducer is not None and getattr(reducer, "split", False)
+        self.split_at = None
+        self._graph2 = None
+        self._split_off = 0
         self._graph = None
         self._sx = self._sy = self._sloss = None
         self._eager_steps = 0
@@ -313,8 +318,57 @@ class Trainer:
         loss.backward()
         return loss.detach()
 
+    def _blocks(self):
+        m = self.model
+        for cand in (m, getattr(m, "backbone", None)):
+            blocks = getattr(cand, "blocks", None) if cand is not None else None
+            if blocks is not None and len(blocks) >= 4 and all(p.requires_grad for p in blocks[0].parameters()):
+                return blocks
+        return None
+
+    def _capture_split(self, x: torch.Tensor, y: torch.Tensor) -> None:
+        """Two graphs: (1) forward + loss + backward down to the input of block `split_at`, (2) the rest of backward.
+        The gradient arena fills in backward order, so graph 1 owns arena[0:_split_off) -- reduced on the side stream
+        while graph 2 replays on grids sized for the SMs NCCL leaves free."""
+        from . import dist as vdist
+        from . import functional, ops
+        blocks = self._blocks()
+        k = self.split_at if self.split_at is not None else max(1, len(blocks) // 3)
+        self.split_at = k
+        stash = {}
+
+        def cut(_mod, args):     # forward pre-hook of block k: cut the autograd graph at its input
+            xk = args[0]
+            xd = xk.detach().requires_grad_(True)
+            stash["xk"], stash["xd"] = xk, xd
+            return (xd,) + tuple(args[1:])
+
+        self._sx, self._sy = x.clone(), y.clone()
+        torch.cuda.synchronize()
+        self._graph, self._graph2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        n0 = ops.launch_count
+        handle = blocks[k].register_forward_pre_hook(cut)
+        try:
+            with torch.cuda.graph(self._graph):
+                self._sloss = self._fwd_bwd(self._sx, self._sy)       # backward stops at the detached input of block k
+            self._split_off = self.arena.off
+            limit = vdist.partition_limit(self.reducer.split_ctas)
+            ops.set_sm_limit(limit)                                   # graph 2 shares the GPU with the side all-reduce
+            try:
+                with torch.cuda.graph(self._graph2, pool=self._graph.pool()):
+                    stash["xk"].backward(stash["xd"].grad)
+            finally:
+                ops.set_sm_limit(0)
+        finally:
+            handle.remove()
+        self.launches_per_step = ops.launch_count - n0 + 1
+        self.reducer.discard_pending()
+        self._static_grads = [(p, p.grad) for p in self.model.parameters() if p.grad is not None]
+
     def _capture(self, x: torch.Tensor, y: torch.Tensor) -> None:
         from . import ops
+        if self.split and self._blocks() is not None and self.arena is not None:
+            return self._capture_split(x, y)
         # (no warm-up step here: it would be an extra optimisation step; step() has already run two eager ones)
         self._sx, self._sy = x.clone(), y.clone()
         if self.opt_in_graph and hasattr(self.opt, "prepare_capture"):
@@ -351,6 +405,15 @@ class Trainer:
         if self.opt_in_graph and hasattr(self.opt, "sync_hyper"):
             self.opt.sync_hyper()       # lr schedules act on the captured step through device-resident hyper-parameters
         self._graph.replay()
+        if self._graph2 is not None:
+            # first half of the gradients: all-reduce on the side stream while the second backward graph runs
+            self.reducer.reduce_first_half(self.arena, self._split_off)
+            self._graph2.replay()
+            for p, g in self._static_grads:
+                p.grad = g
+            self.reducer.reduce_second_half(self.arena, self._split_off)
+            self.opt.step()
+            return self._sloss
         if not self.opt_in_graph:
             self._finish_static()
         return self._sloss
