@@ -136,6 +136,7 @@ class GradAllReducer:
         if arena.off > start:
             dist.all_reduce(arena.buf[start:arena.off], op=dist.ReduceOp.AVG, group=self.pg)
             self.collectives += 1
+        self._reduce_rest(arena.buf.untyped_storage().data_ptr())
         if self._side_done is not None:
             torch.cuda.current_stream().wait_event(self._side_done)
             self._side_done = None
@@ -168,8 +169,14 @@ class GradAllReducer:
         if arena is not None and arena.off > 0:
             self._reduce_arena(arena)
             base = arena.buf.untyped_storage().data_ptr()
+        self._reduce_rest(base)
+
+    def _reduce_rest(self, arena_base) -> None:
+        """All-reduce (average) the gradients that do not live in the arena (e.g. pos_embed when its gradient comes back
+        through torch's interpolate for an input that is not the training resolution)."""
+        op = dist.ReduceOp.AVG if self.cuda else dist.ReduceOp.SUM
         rest = [p.grad for p in self.model.parameters()
-                if p.grad is not None and (base is None or p.grad.untyped_storage().data_ptr() != base)]
+                if p.grad is not None and (arena_base is None or p.grad.untyped_storage().data_ptr() != arena_base)]
         if rest:
             flat = torch.cat([g.reshape(-1) for g in rest])
             dist.all_reduce(flat, op=op, group=self.pg)

@@ -341,6 +341,9 @@ class Trainer:
             xk = args[0]
             xd = xk.detach().requires_grad_(True)
             stash["xk"], stash["xd"] = xk, xd
+            # keep the gradient OBJECT block k's backward returns: it carries the bf16 copy / column sums that the next
+            # block's backward reuses (functional.BlockFn side channel); .grad would be a bare alias of it
+            xd.register_hook(lambda g: stash.__setitem__("g", g))
             return (xd,) + tuple(args[1:])
 
         self._sx, self._sy = x.clone(), y.clone()
@@ -356,7 +359,7 @@ class Trainer:
             ops.set_sm_limit(limit)                                   # graph 2 shares the GPU with the side all-reduce
             try:
                 with torch.cuda.graph(self._graph2, pool=self._graph.pool()):
-                    stash["xk"].backward(stash["xd"].grad)
+                    stash["xk"].backward(stash.get("g", stash["xd"].grad))
             finally:
                 ops.set_sm_limit(0)
         finally:
