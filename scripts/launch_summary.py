@@ -2,7 +2,7 @@
 
     python scripts/launch_summary.py gpurun_out/launches.csv [step_index]
 
-A step starts at each patchify_kernel launch (first kernel of the forward pass)."""
+A step starts at the first kernel of the forward pass (normalize_u8 / patch_embed_fwd / patchify)."""
 import csv, re, collections, sys
 rows = list(csv.reader(open(sys.argv[1])))
 for i, r in enumerate(rows):
@@ -15,7 +15,9 @@ for r in rows[start + 1:]:
     v = float(r[ci['Metric Value']].replace(',', '')); unit = r[ci['Metric Unit']]
     v = v / 1000 if unit == 'ns' else v * 1000 if unit == 'ms' else v
     L.append((r[ci['Kernel Name']], r[ci['Grid Size']], r[ci['Block Size']], v))
-idx = [i for i, l in enumerate(L) if 'patchify' in l[0] or 'patch_embed' in l[0]]
+first = ('normalize_u8', 'patchify', 'patch_embed_fwd')   # first kernel of a step's forward pass
+idx = [i for i, l in enumerate(L) if any(f in l[0] for f in first)]
+idx = [i for j, i in enumerate(idx) if j == 0 or i - idx[j - 1] > 3]   # normalize_u8 is followed by patch_embed_fwd
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 step = L[idx[k]:idx[k + 1]] if k + 1 < len(idx) else L[idx[k]:]
 tot = sum(l[3] for l in step)
