@@ -274,6 +274,32 @@ int vitk_th_mix_bwd_bf16(const float* S, const void* dPm_bf16, const float* rowm
                          const float* bl, const float* ww, const float* bw, float scale, void* dS_bf16, float* dwl,
                          float* dbl, float* dww, float* dbw, int B, int H, int N, int Np, void* stream);
 
+/* bf16 logit planes S bf16 [B,H,N,Np] -- what the reference's `q @ k.transpose(-2, -1)` produces under
+ * torch.autocast(bfloat16) (models/cait.py:116) -- with the version-2 mixing kernels; otherwise as vitk_th_mix_fwd /
+ * vitk_th_mix_bwd_bf16 (bf16 values are exact in tf32, so the 3xTF32 logit mix drops to two products). */
+int vitk_th_mix_fwd_s16(const void* S_bf16, const float* wl, const float* bl, const float* ww, const float* bw, float scale,
+                        void* Pm_bf16, float* rowmax, float* rowsum, int B, int H, int N, int Np, void* stream);
+int vitk_th_mix_bwd_s16(const void* S_bf16, const void* dPm_bf16, const float* rowmax, const float* rowsum, const float* wl,
+                        const float* bl, const float* ww, const float* bw, float scale, void* dS_bf16, float* dwl,
+                        float* dbl, float* dww, float* dbw, int B, int H, int N, int Np, void* stream);
+
+/*
+ * The per-(image, head) products around the talking-heads mixes (models/cait.py:116 `q @ k^T`, :125 `attn @ v`, and
+ * their autograd) for short sequences: N <= 208 tokens, d in {48, 64}, Np % 8 == 0 (vitk_th_gemm_supported). Operands
+ * are token-major bf16 matrices [B*N, ld] read in place (head h = columns col0 + h*d .. + d of a matrix that has
+ * `cols` valid columns) and planes [B,H,N,Np]:
+ *   vitk_th_scores : out[b,h,i,j] = sum_e a[b*N+i, a_col0+h*d+e] * b[b*N+j, b_col0+h*d+e]   (out bf16, or fp32 if out_f32;
+ *                    pad columns [N, Np) are written as zeros)
+ *   vitk_th_apply  : out[b*N+i, o_col0+h*d+e] = sum_j p[b,h,i,j] * x[b*N+j, x_col0+h*d+e]    (transpose = 0)
+ *                    out[b*N+j, o_col0+h*d+e] = sum_i p[b,h,i,j] * x[b*N+i, x_col0+h*d+e]    (transpose = 1)
+ *                    p bf16 planes whose pad columns are zero (as vitk_th_mix_* write them); out bf16 [B*N, ldo].
+ */
+int vitk_th_gemm_supported(int N, int d, int Np);
+int vitk_th_scores(const void* a_bf16, long long lda, int a_cols, int a_col0, const void* b_bf16, long long ldb, int b_cols,
+                   int b_col0, void* out, int out_f32, int B, int N, int H, int d, int Np, void* stream);
+int vitk_th_apply(const void* p_bf16, const void* x_bf16, long long ldx, int x_cols, int x_col0, void* out_bf16,
+                  long long ldo, int o_col0, int transpose, int B, int N, int H, int d, int Np, void* stream);
+
 /*
  * CaiT class attention (models/cait.py:38-55): one query row per (image, head). q bf16 [B,C] (unscaled), keys/values:
  * row 0 = class token kc/vc bf16 [B, ldc], rows 1..n = patch tokens kx/vx bf16 [B*n, ldkv]. out bf16 [B,C];

@@ -455,35 +455,81 @@ static bool th2_enabled(int Np) {
     if (v1 < 0) { const char* e = getenv("VITK_TH_MIX"); v1 = (e != nullptr && e[0] == '1') ? 1 : 0; }
     return !v1 && Np <= 16 * TH2_MAX_TILES;
 }
-template <int H> static int th2_fwd_launch(const float* S, const float* wl, const float* bl, const float* ww,
+template <int H, typename ST> static int th2_fwd_launch(const ST* S, const float* wl, const float* bl, const float* ww,
                                            const float* bw, float scale, __nv_bfloat16* Pm, float* rmax, float* rsum,
                                            int B, int N, int Np, cudaStream_t st) {
     const long long rows = (long long)B * N;
     long long grid = (rows + TH2_WARPS - 1) / TH2_WARPS;
     const long long cap = (long long)sm_count() * 4;
     if (grid > cap) grid = cap;
-    if (Np <= 64) th_mix2_fwd_kernel<H, 4><<<(unsigned)grid, TH2_WARPS * 32, 0, st>>>(S, wl, bl, ww, bw, scale, Pm, rmax, rsum, B, N, Np);
-    else th_mix2_fwd_kernel<H, TH2_MAX_TILES><<<(unsigned)grid, TH2_WARPS * 32, 0, st>>>(S, wl, bl, ww, bw, scale, Pm, rmax, rsum, B, N, Np);
+    if (Np <= 64) th_mix2_fwd_kernel<H, 4, ST><<<(unsigned)grid, TH2_WARPS * 32, 0, st>>>(S, wl, bl, ww, bw, scale, Pm, rmax, rsum, B, N, Np);
+    else th_mix2_fwd_kernel<H, TH2_MAX_TILES, ST><<<(unsigned)grid, TH2_WARPS * 32, 0, st>>>(S, wl, bl, ww, bw, scale, Pm, rmax, rsum, B, N, Np);
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
 }
-template <int H> static int th2_bwd_launch(const float* S, const __nv_bfloat16* dPm, const float* rmax, const float* rsum,
-                                           const float* wl, const float* bl, const float* ww, float scale,
-                                           __nv_bfloat16* dS, float* dwl, float* dbl, float* dww, float* dbw, int B, int N,
-                                           int Np, cudaStream_t st) {
+// VITK_TH_BWD = 0: original form (8 warps, 1 block / SM) | 1: lean, 8 warps x 2 blocks | 2: lean, 12 warps x 1 block (default for
+// bf16 planes). fp32 planes always run the original form.
+static int th2_bwd_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VITK_TH_BWD"); v = e ? atoi(e) : 2; if (v < 0 || v > 2) v = 2; }
+    return v;
+}
+template <int H, typename ST, int WARPS, int MINB, bool LEAN>
+static int th2_bwd_launch_v(const ST* S, const __nv_bfloat16* dPm, const float* rmax, const float* rsum, const float* wl,
+                            const float* bl, const float* ww, float scale, __nv_bfloat16* dS, float* dwl, float* dbl,
+                            float* dww, float* dbw, int B, int N, int Np, cudaStream_t st) {
     const long long rows = (long long)B * N;
-    long long grid = (rows + TH2_WARPS - 1) / TH2_WARPS;
-    const long long cap = (long long)sm_count() * 1;      // 1 block / SM (register budget); persistent over rows
+    long long grid = (rows + WARPS - 1) / WARPS;
+    const long long cap = (long long)sm_count() * MINB;      // persistent over rows
     if (grid > cap) grid = cap;
     if (Np <= 64)
-        th_mix2_bwd_kernel<H, 4><<<(unsigned)grid, TH2_WARPS * 32, 0, st>>>(S, dPm, rmax, rsum, wl, bl, ww, scale, dS, dwl,
-                                                                           dbl, dww, dbw, B, N, Np);
+        th_mix2_bwd_kernel<H, 4, ST, WARPS, MINB, LEAN><<<(unsigned)grid, WARPS * 32, 0, st>>>(
+            S, dPm, rmax, rsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np);
     else
-        th_mix2_bwd_kernel<H, TH2_MAX_TILES><<<(unsigned)grid, TH2_WARPS * 32, 0, st>>>(S, dPm, rmax, rsum, wl, bl, ww, scale,
-                                                                                       dS, dwl, dbl, dww, dbw, B, N, Np);
+        th_mix2_bwd_kernel<H, TH2_MAX_TILES, ST, WARPS, MINB, LEAN><<<(unsigned)grid, WARPS * 32, 0, st>>>(
+            S, dPm, rmax, rsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np);
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+template <int H, typename ST> static int th2_bwd_launch(const ST* S, const __nv_bfloat16* dPm, const float* rmax, const float* rsum,
+                                                        const float* wl, const float* bl, const float* ww, float scale,
+                                                        __nv_bfloat16* dS, float* dwl, float* dbl, float* dww, float* dbw,
+                                                        int B, int N, int Np, cudaStream_t st) {
+    if constexpr (sizeof(ST) == 2) {
+        const int v = th2_bwd_variant();
+        if (v == 1) return th2_bwd_launch_v<H, ST, 8, 2, true>(S, dPm, rmax, rsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
+        if constexpr (H <= 8) {     // (16 heads: the per-warp transposition scratch of 12 warps exceeds 48 KB)
+            if (v == 2) return th2_bwd_launch_v<H, ST, 12, 1, true>(S, dPm, rmax, rsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
+        }
+    }
+    return th2_bwd_launch_v<H, ST, 8, 1, false>(S, dPm, rmax, rsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
 }
 
 extern "C" int vitk_th_mix_supports_bf16_dp(int Np) { return th2_enabled(Np) ? 1 : 0; }
+
+template <typename ST>
+static int th2_bwd_dispatch(const ST* S, const __nv_bfloat16* dP, const float* rowmax, const float* rowsum, const float* wl,
+                            const float* bl, const float* ww, float scale, __nv_bfloat16* dS, float* dwl, float* dbl,
+                            float* dww, float* dbw, int B, int H, int N, int Np, cudaStream_t st) {
+    switch (H) {
+        case 2: return th2_bwd_launch<2, ST>(S, dP, rowmax, rowsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
+        case 4: return th2_bwd_launch<4, ST>(S, dP, rowmax, rowsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
+        case 6: return th2_bwd_launch<6, ST>(S, dP, rowmax, rowsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
+        case 8: return th2_bwd_launch<8, ST>(S, dP, rowmax, rowsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
+        case 16: return th2_bwd_launch<16, ST>(S, dP, rowmax, rowsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
+        default: return VITK_ERR_UNSUPPORTED;
+    }
+}
+template <typename ST>
+static int th2_fwd_dispatch(const ST* S, const float* wl, const float* bl, const float* ww, const float* bw, float scale,
+                            __nv_bfloat16* P, float* rowmax, float* rowsum, int B, int H, int N, int Np, cudaStream_t st) {
+    switch (H) {
+        case 2: return th2_fwd_launch<2, ST>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);
+        case 4: return th2_fwd_launch<4, ST>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);
+        case 6: return th2_fwd_launch<6, ST>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);
+        case 8: return th2_fwd_launch<8, ST>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);
+        case 16: return th2_fwd_launch<16, ST>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);
+        default: return VITK_ERR_UNSUPPORTED;
+    }
+}
 
 extern "C" int vitk_th_mix_bwd_bf16(const float* S, const void* dPm_bf16, const float* rowmax, const float* rowsum,
                                     const float* wl, const float* bl, const float* ww, const float* bw, float scale,
@@ -493,17 +539,35 @@ extern "C" int vitk_th_mix_bwd_bf16(const float* S, const void* dPm_bf16, const 
         !dS_bf16 || !dwl || !dbl || !dww || !dbw)
         return VITK_ERR_ARG;
     if (!th2_enabled(Np)) return VITK_ERR_UNSUPPORTED;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    auto dP = reinterpret_cast<const __nv_bfloat16*>(dPm_bf16);
-    auto dS = reinterpret_cast<__nv_bfloat16*>(dS_bf16);
-    switch (H) {
-        case 2: return th2_bwd_launch<2>(S, dP, rowmax, rowsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
-        case 4: return th2_bwd_launch<4>(S, dP, rowmax, rowsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
-        case 6: return th2_bwd_launch<6>(S, dP, rowmax, rowsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
-        case 8: return th2_bwd_launch<8>(S, dP, rowmax, rowsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
-        case 16: return th2_bwd_launch<16>(S, dP, rowmax, rowsum, wl, bl, ww, scale, dS, dwl, dbl, dww, dbw, B, N, Np, st);
-        default: return VITK_ERR_UNSUPPORTED;
-    }
+    return th2_bwd_dispatch<float>(S, reinterpret_cast<const __nv_bfloat16*>(dPm_bf16), rowmax, rowsum, wl, bl, ww, scale,
+                                   reinterpret_cast<__nv_bfloat16*>(dS_bf16), dwl, dbl, dww, dbw, B, H, N, Np,
+                                   reinterpret_cast<cudaStream_t>(stream));
+}
+
+// bf16 logit planes (what the reference's matmul produces under torch.autocast(bfloat16)): version-2 kernels only
+extern "C" int vitk_th_mix_fwd_s16(const void* S_bf16, const float* wl, const float* bl, const float* ww, const float* bw,
+                                   float scale, void* Pm_bf16, float* rowmax, float* rowsum, int B, int H, int N, int Np,
+                                   void* stream) {
+    if (B <= 0 || N <= 0 || Np < N || (Np % 8) != 0 || !S_bf16 || !wl || !bl || !ww || !bw || !Pm_bf16 || !rowmax || !rowsum)
+        return VITK_ERR_ARG;
+    if (!th2_enabled(Np)) return VITK_ERR_UNSUPPORTED;
+    return th2_fwd_dispatch<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(S_bf16), wl, bl, ww, bw, scale,
+                                           reinterpret_cast<__nv_bfloat16*>(Pm_bf16), rowmax, rowsum, B, H, N, Np,
+                                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vitk_th_mix_bwd_s16(const void* S_bf16, const void* dPm_bf16, const float* rowmax, const float* rowsum,
+                                   const float* wl, const float* bl, const float* ww, const float* bw, float scale,
+                                   void* dS_bf16, float* dwl, float* dbl, float* dww, float* dbw, int B, int H, int N,
+                                   int Np, void* stream) {
+    if (B <= 0 || N <= 0 || Np < N || (Np % 8) != 0 || !S_bf16 || !dPm_bf16 || !rowmax || !rowsum || !wl || !bl || !ww ||
+        !bw || !dS_bf16 || !dwl || !dbl || !dww || !dbw)
+        return VITK_ERR_ARG;
+    if (!th2_enabled(Np)) return VITK_ERR_UNSUPPORTED;
+    return th2_bwd_dispatch<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(S_bf16),
+                                           reinterpret_cast<const __nv_bfloat16*>(dPm_bf16), rowmax, rowsum, wl, bl, ww,
+                                           scale, reinterpret_cast<__nv_bfloat16*>(dS_bf16), dwl, dbl, dww, dbw, B, H, N, Np,
+                                           reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vitk_th_mix_fwd(const float* S, const float* wl, const float* bl, const float* ww, const float* bw,
@@ -513,16 +577,7 @@ extern "C" int vitk_th_mix_fwd(const float* S, const float* wl, const float* bl,
         return VITK_ERR_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     auto P = reinterpret_cast<__nv_bfloat16*>(Pm_bf16);
-    if (th2_enabled(Np)) {
-        switch (H) {
-            case 2: return th2_fwd_launch<2>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);
-            case 4: return th2_fwd_launch<4>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);
-            case 6: return th2_fwd_launch<6>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);
-            case 8: return th2_fwd_launch<8>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);
-            case 16: return th2_fwd_launch<16>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);
-            default: return VITK_ERR_UNSUPPORTED;
-        }
-    }
+    if (th2_enabled(Np)) return th2_fwd_dispatch<float>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, H, N, Np, st);
     switch (H) {
         case 4: return th_fwd_launch<4>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);
         case 6: return th_fwd_launch<6>(S, wl, bl, ww, bw, scale, P, rowmax, rowsum, B, N, Np, st);

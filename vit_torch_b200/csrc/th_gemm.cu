@@ -1,0 +1,423 @@
+// Short-sequence per-(image, head) products of the talking-heads attention path (models/cait.py:111-128, and the
+// autograd of the same), N <= 208 tokens (CaiT at 224 px: 196), head dim 48 or 64, on tcgen05:
+//
+//   th_scores : S[b,h,i,j]   = sum_e A[b,i,h,e] * Bm[b,j,h,e]      (q k^T  and  dO v^T : bf16 / fp32 planes [B,H,N,Np])
+//   th_apply  : O[b,i,(h,e)] = sum_j P[b,h,i,j] * X[b,j,(h,e)]     (P' v   and  dS k   : token-major bf16)
+//   th_apply_t: O[b,j,(h,e)] = sum_i P[b,h,i,j] * X[b,i,(h,e)]     (P'^T dO and dS^T q : token-major bf16)
+//
+// The talking-heads mixes couple all heads of a (query, key) position, so the [B,H,N,N] planes exist in HBM between
+// these products and the mixing kernels (th_mix2.cuh); what this file fixes is the cost of the products themselves.
+// The generic batched GEMM ran them as 128 x 128 tiles with one 64-deep k-block each behind rank-4 tensor maps -- a
+// latency-bound pipeline of thousands of tiny tiles. Here a thread block owns one (image, 128-row block) and walks the
+// heads: whole-image operand tiles (<= 208 rows) arrive through rank-3 maps {columns, N, image or plane} whose
+// out-of-range rows are ZERO-filled (so the contraction tail needs no masking), one head = one accumulator, and
+//   * th_scores drains the 128 x 208 accumulator of head h while the operands of head h+1 are in flight,
+//   * th_apply / th_apply_t keep the outputs of up to 8 heads side by side in TMEM and write whole token rows once.
+// Each kernel is bounded by HBM: it reads / writes every plane element exactly once.
+#include <cstdlib>
+#include "common.cuh"
+#include "tmap.cuh"
+#include "../../include/vitk.h"
+
+namespace vitk {
+
+constexpr int TG_THREADS = 320;                 // warps 0-7 epilogue, warp 8 TMA, warp 9 MMA
+constexpr int TG_ROWS = 208;                    // rows of a whole-image operand tile (tokens, padded to 16)
+constexpr int TG_T128 = 128 * 128;              // [128 rows x 64 bf16] swizzled tile bytes
+constexpr int TG_TIMG = TG_ROWS * 128;          // [208 rows x 64 bf16] swizzled tile bytes (26 x 1024)
+constexpr int TG_NS = 2;                        // operand stages (heads in flight)
+
+struct ThGemmArgs {
+    int B, H, N, Np;        // Np: row pitch of a plane (multiple of 8)
+    int HG;                 // heads per thread block
+    int a_col0, b_col0;     // first column of head 0 inside the token-major operands
+    void* out;              // th_scores: plane [B,H,N,Np] (bf16 or fp32); th_apply*: token-major bf16 [B*N, ldo]
+    long long ldo;
+    int o_col0;
+    int out_f32;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// th_scores: grid (row blocks, head groups, B). Stage = A tile [128 x 64] + B tile [208 x 64]; one accumulator
+// [128 x 208] fp32 in TMEM (256 columns allocated: two thread blocks per SM).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int TS_STAGE = TG_T128 + TG_TIMG;                 // 43008
+constexpr int TS_SMEM_BAR = TG_NS * TS_STAGE;
+constexpr int TS_SMEM_BYTES = TS_SMEM_BAR + 128;
+
+template <int HD>
+__global__ void __launch_bounds__(TG_THREADS, 2)
+th_scores_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ThGemmArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TS_SMEM_BAR);
+    uint64_t* full = bars;               // [TG_NS]
+    uint64_t* empty = bars + TG_NS;      // [TG_NS]
+    uint64_t* acc_full = bars + 2 * TG_NS;
+    uint64_t* acc_free = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, b = blockIdx.z;
+    const int h0 = blockIdx.y * a.HG, h1 = min(a.H, h0 + a.HG);
+    const int nk16 = (a.N + 15) & ~15;                     // UMMA N (<= 208)
+
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
+    if (warp == 8 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < TG_NS; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_free, 256);
+        fence_mbar_init();
+    }
+    if (warp == 9) tmem_alloc<256>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            int it = 0;
+            for (int h = h0; h < h1; ++h, ++it) {
+                const int s = it % TG_NS;
+                if (it >= TG_NS) mbar_wait_backoff(&empty[s], ((it / TG_NS) & 1) ^ 1);
+                uint8_t* st = smem + s * TS_STAGE;
+                mbar_expect_tx(&full[s], TS_STAGE);
+                tma_load_3d(st, &tmA, &full[s], a.a_col0 + h * HD, q0, b);
+                tma_load_3d(st + TG_T128, &tmB, &full[s], a.b_col0 + h * HD, 0, b);
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, (uint32_t)nk16, 0, 0);
+            int it = 0;
+            for (int h = h0; h < h1; ++h, ++it) {
+                const int s = it % TG_NS;
+                mbar_wait_backoff(&full[s], (it / TG_NS) & 1);
+                if (it > 0) mbar_wait_backoff(acc_free, (it - 1) & 1);
+                tc_fence_after_sync();
+                const uint32_t sa = smem_u32(smem + s * TS_STAGE);
+                const uint64_t adesc = make_smem_desc_sw128(sa, 0, 1024);
+                const uint64_t bdesc = make_smem_desc_sw128(sa + TG_T128, 0, 1024);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
+                umma_commit(&empty[s]);
+                umma_commit(acc_full);
+            }
+        }
+    } else {
+        // epilogue: lane quadrant = rows, warp half = columns [0,112) / [112,208)
+        const int q = warp & 3, half = warp >> 2;
+        const int row = q0 + q * 32 + lane;
+        const bool row_ok = row < a.N;
+        const uint32_t lane_off = uint32_t(q * 32) << 16;
+        const int c_begin = half ? 112 : 0, c_end = half ? TG_ROWS : 112;
+        const int esz = a.out_f32 ? 4 : 2;
+        int it = 0;
+        for (int h = h0; h < h1; ++h, ++it) {
+            mbar_wait(acc_full, it & 1);
+            tc_fence_after_sync();
+            uint8_t* orow = reinterpret_cast<uint8_t*>(a.out) +
+                            ((((long long)b * a.H + h) * a.N + row) * (long long)a.Np) * esz;
+            uint32_t r[2][16];
+            if (c_begin < nk16) tmem_ld_32x32b_x16(tmem_base + lane_off + c_begin, r[0]);
+            int pb = 0;
+            for (int c = c_begin; c < c_end; c += 16, pb ^= 1) {
+                if (c >= nk16) break;                      // (warp-uniform) nothing computed past the padded key count
+                tmem_ld_wait();
+                if (c + 16 < c_end && c + 16 < nk16) tmem_ld_32x32b_x16(tmem_base + lane_off + c + 16, r[pb ^ 1]);
+                const uint32_t* v = r[pb];
+                if (row_ok) {
+                    if (a.out_f32) {
+                        float* o = reinterpret_cast<float*>(orow) + c;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (c + 4 * u + 4 <= a.Np)
+                                st_v4(o + 4 * u, make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
+                    } else {
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(orow) + c;
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+                            if (c + 8 * u + 8 <= a.Np)
+                                st_v4(o + 8 * u,
+                                      make_uint4(pack_bf16(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
+                                                 pack_bf16(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
+                                                 pack_bf16(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
+                                                 pack_bf16(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7]))));
+                    }
+                }
+            }
+            tmem_ld_wait();
+            tc_fence_before_sync();
+            mbar_arrive(acc_free);
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after_sync();
+        tmem_dealloc<256>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// th_apply (TRANS = false): grid (row blocks of i, head groups, B). Stage = P rows [128 x 256 columns] as four K-major
+//   tiles + X_h [208 x 64] (MN-major B operand).
+// th_apply_t (TRANS = true): grid (column blocks of j, head groups, B). Stage = P columns [208 rows x 128 columns] as
+//   two MN-major tiles + X_h [208 x 64] (MN-major B operand).
+// The outputs of the block's heads sit side by side in TMEM (HG * HD <= 512 columns) and leave once, as whole token rows.
+// ------------------------------------------------------------------------------------------------------------------
+// Two shapes of the same kernel (VITK_TH_APPLY picks one for A/B runs): NS = 2 operand stages, up to 8 heads = 512 TMEM
+// columns, one thread block per SM | NS = 1, up to 4 heads = 256 columns, two thread blocks per SM.
+template <bool TRANS, int NS> struct TaCfg {
+    static constexpr int A_BYTES = TRANS ? 2 * TG_TIMG : 4 * TG_T128;      // 53248 / 65536
+    static constexpr int STAGE = A_BYTES + TG_TIMG;
+    static constexpr int SMEM_BAR = NS * STAGE;
+    static constexpr int SMEM_BYTES = SMEM_BAR + 128;
+};
+
+template <int HD, bool TRANS, int NS>
+__global__ void __launch_bounds__(TG_THREADS, (NS == 1 ? 2 : 1))
+th_apply_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmX, const ThGemmArgs a) {
+    using Cfg = TaCfg<TRANS, NS>;
+    constexpr uint32_t TCOLS = NS == 1 ? 256 : 512;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::SMEM_BAR);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + NS;
+    uint64_t* acc_full = bars + 2 * NS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * 128, b = blockIdx.z;
+    const int h0 = blockIdx.y * a.HG, h1 = min(a.H, h0 + a.HG);
+    const int nks = (a.N + 15) >> 4;                        // k-steps over the contracted token axis (<= 13)
+
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
+    if (warp == 8 && lane == 0) {
+        tma_prefetch_desc(&tmP);
+        tma_prefetch_desc(&tmX);
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 9) tmem_alloc<TCOLS>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            int it = 0;
+            for (int h = h0; h < h1; ++h, ++it) {
+                const int s = it % NS;
+                if (it >= NS) mbar_wait_backoff(&empty[s], ((it / NS) & 1) ^ 1);
+                uint8_t* st = smem + s * Cfg::STAGE;
+                const int plane = b * a.H + h;
+                if constexpr (!TRANS) {
+                    // columns past Np and rows past N arrive as zeros; tiles whose first column is >= Np are not fetched
+                    const int nchunk = min(4, (a.Np + 63) >> 6);
+                    mbar_expect_tx(&full[s], nchunk * TG_T128 + TG_TIMG);
+                    for (int c = 0; c < nchunk; ++c) tma_load_3d(st + c * TG_T128, &tmP, &full[s], 64 * c, m0, plane);
+                } else {
+                    const int nchunk = (m0 + 64 < a.Np) ? 2 : 1;
+                    mbar_expect_tx(&full[s], nchunk * TG_TIMG + TG_TIMG);
+                    for (int c = 0; c < nchunk; ++c) tma_load_3d(st + c * TG_TIMG, &tmP, &full[s], m0 + 64 * c, 0, plane);
+                }
+                tma_load_3d(st + Cfg::A_BYTES, &tmX, &full[s], a.b_col0 + h * HD, 0, b);
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, HD, TRANS ? 1u : 0u, 1u);
+            int it = 0;
+            for (int h = h0; h < h1; ++h, ++it) {
+                const int s = it % NS;
+                mbar_wait_backoff(&full[s], (it / NS) & 1);
+                tc_fence_after_sync();
+                const uint32_t sa = smem_u32(smem + s * Cfg::STAGE), sb = sa + Cfg::A_BYTES;
+                const uint32_t tmem_d = tmem_base + (uint32_t)(it * HD);
+                for (int k = 0; k < nks; ++k) {
+                    uint64_t adesc;
+                    if constexpr (!TRANS)   // K-major: k-step k = 16 columns = tile k / 4, +32 B per step inside the tile
+                        adesc = make_smem_desc_sw128(sa + (k >> 2) * TG_T128 + (k & 3) * 32, 0, 1024);
+                    else                    // MN-major: two 64-wide column chunks TG_TIMG apart, +16 rows per k-step
+                        adesc = make_smem_desc_sw128(sa + k * 2048, TG_TIMG, 1024);
+                    const uint64_t bdesc = make_smem_desc_sw128(sb + k * 2048, TG_TIMG, 1024);
+                    umma_bf16(tmem_d, adesc, bdesc, idesc, k > 0 ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        const int q = warp & 3, half = warp >> 2;
+        const int row = m0 + q * 32 + lane;
+        const bool row_ok = row < a.N;
+        const uint32_t lane_off = uint32_t(q * 32) << 16;
+        const int ncols = (h1 - h0) * HD;                      // multiple of 16
+        const int nch = ncols >> 4;
+        const int ch0 = half ? (nch + 1) / 2 : 0, ch1 = half ? nch : (nch + 1) / 2;
+        mbar_wait(acc_full, 0);
+        tc_fence_after_sync();
+        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(a.out) + ((long long)b * a.N + row) * a.ldo + a.o_col0 +
+                              h0 * HD;
+        auto store16 = [&](int ch, const uint32_t* v) {      // 16 columns of this lane's row -> 32 bytes of bf16
+            if (!row_ok) return;
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                st_v4(orow + ch * 16 + 8 * u,
+                      make_uint4(pack_bf16(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
+                                 pack_bf16(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
+                                 pack_bf16(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
+                                 pack_bf16(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7]))));
+        };
+        int ch = ch0;
+        for (; ch + 2 <= ch1; ch += 2) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_off + ch * 16, r);
+            tmem_ld_wait();
+            store16(ch, r);
+            store16(ch + 1, r + 16);
+        }
+        if (ch < ch1) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tmem_base + lane_off + ch * 16, r);
+            tmem_ld_wait();
+            store16(ch, r);
+        }
+        tmem_ld_wait();
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after_sync();
+        tmem_dealloc<TCOLS>(tmem_base);
+    }
+}
+
+// rank-3 bf16 map {columns, rows, slabs} with byte strides {row pitch, slab pitch}; box {64 columns, box_rows, 1}.
+static int make_tmap_3d_rows(CUtensorMap* out, const void* p, uint64_t cols, uint64_t rows, uint64_t slabs,
+                             uint64_t row_pitch_elems, uint64_t slab_pitch_elems, uint32_t box_rows) {
+    uint64_t dims[3] = {cols, rows, slabs};
+    uint64_t strides[2] = {row_pitch_elems * 2, slab_pitch_elems * 2};
+    uint32_t box[3] = {64, box_rows, 1};
+    return make_tmap(out, p, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+}
+
+static bool th_gemm_shape_ok(int B, int N, int H, int d, int Np) {
+    return B > 0 && H > 0 && N > 0 && N <= TG_ROWS && (d == 48 || d == 64) && Np >= N && (Np % 8) == 0 && Np <= 256;
+}
+
+template <int HD>
+static int launch_th_scores(const void* A, long long lda, int a_cols, const void* Bm, long long ldb, int b_cols,
+                            const ThGemmArgs& a, cudaStream_t st) {
+    CUtensorMap tmA, tmB;
+    if (make_tmap_3d_rows(&tmA, A, (uint64_t)a_cols, (uint64_t)a.N, (uint64_t)a.B, (uint64_t)lda, (uint64_t)lda * a.N, 128) ||
+        make_tmap_3d_rows(&tmB, Bm, (uint64_t)b_cols, (uint64_t)a.N, (uint64_t)a.B, (uint64_t)ldb, (uint64_t)ldb * a.N, TG_ROWS))
+        return VITK_ERR_TMAP;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(th_scores_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES) !=
+            cudaSuccess)
+            return VITK_ERR_CUDA;
+        attr = true;
+    }
+    dim3 grid((a.N + 127) / 128, (a.H + a.HG - 1) / a.HG, a.B);
+    th_scores_kernel<HD><<<grid, TG_THREADS, TS_SMEM_BYTES, st>>>(tmA, tmB, a);
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
+template <int HD, bool TRANS, int NS>
+static int launch_th_apply(const void* P, const void* X, long long ldx, int x_cols, const ThGemmArgs& a, cudaStream_t st) {
+    CUtensorMap tmP, tmX;
+    if (make_tmap_3d_rows(&tmP, P, (uint64_t)a.Np, (uint64_t)a.N, (uint64_t)a.B * a.H, (uint64_t)a.Np,
+                          (uint64_t)a.Np * a.N, TRANS ? TG_ROWS : 128) ||
+        make_tmap_3d_rows(&tmX, X, (uint64_t)x_cols, (uint64_t)a.N, (uint64_t)a.B, (uint64_t)ldx, (uint64_t)ldx * a.N, TG_ROWS))
+        return VITK_ERR_TMAP;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(th_apply_kernel<HD, TRANS, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 TaCfg<TRANS, NS>::SMEM_BYTES) != cudaSuccess)
+            return VITK_ERR_CUDA;
+        attr = true;
+    }
+    dim3 grid((a.N + 127) / 128, (a.H + a.HG - 1) / a.HG, a.B);
+    th_apply_kernel<HD, TRANS, NS><<<grid, TG_THREADS, TaCfg<TRANS, NS>::SMEM_BYTES, st>>>(tmP, tmX, a);
+    return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
+}
+
+// VITK_TH_APPLY = 2 (default): two stages, <= 8 heads per block, 1 block / SM | 1: one stage, <= 4 heads, 2 blocks / SM
+static int th_apply_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VITK_TH_APPLY"); v = (e && e[0] == '1') ? 1 : 2; }
+    return v;
+}
+
+}  // namespace vitk
+
+using namespace vitk;
+
+extern "C" int vitk_th_gemm_supported(int N, int d, int Np) {
+    return th_gemm_shape_ok(1, N, 1, d, Np) ? 1 : 0;
+}
+
+extern "C" int vitk_th_scores(const void* a_bf16, long long lda, int a_cols, int a_col0, const void* b_bf16,
+                              long long ldb, int b_cols, int b_col0, void* out, int out_f32, int B, int N, int H, int d,
+                              int Np, void* stream) {
+    if (!a_bf16 || !b_bf16 || !out || !th_gemm_shape_ok(B, N, H, d, Np)) return VITK_ERR_ARG;
+    if ((lda % 8) != 0 || (ldb % 8) != 0 || a_col0 < 0 || b_col0 < 0 || a_col0 + H * d > a_cols || b_col0 + H * d > b_cols ||
+        a_cols > lda || b_cols > ldb)
+        return VITK_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(a_bf16) | reinterpret_cast<uintptr_t>(b_bf16) | reinterpret_cast<uintptr_t>(out)) & 15)
+        return VITK_ERR_ARG;
+    ThGemmArgs a;
+    a.B = B; a.H = H; a.N = N; a.Np = Np;
+    a.HG = H <= 4 ? H : (H + 1) / 2;        // two head groups: 2 x row blocks x B thread blocks keep every SM busy
+    a.a_col0 = a_col0; a.b_col0 = b_col0;
+    a.out = out; a.ldo = Np; a.o_col0 = 0; a.out_f32 = out_f32 ? 1 : 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (d == 64) return launch_th_scores<64>(a_bf16, lda, a_cols, b_bf16, ldb, b_cols, a, st);
+    return launch_th_scores<48>(a_bf16, lda, a_cols, b_bf16, ldb, b_cols, a, st);
+}
+
+extern "C" int vitk_th_apply(const void* p_bf16, const void* x_bf16, long long ldx, int x_cols, int x_col0, void* out_bf16,
+                             long long ldo, int o_col0, int transpose, int B, int N, int H, int d, int Np, void* stream) {
+    if (!p_bf16 || !x_bf16 || !out_bf16 || !th_gemm_shape_ok(B, N, H, d, Np)) return VITK_ERR_ARG;
+    if ((ldx % 8) != 0 || (ldo % 8) != 0 || (o_col0 % 8) != 0 || x_col0 < 0 || x_col0 + H * d > x_cols || x_cols > ldx ||
+        o_col0 < 0 || o_col0 + H * d > ldo)
+        return VITK_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(p_bf16) | reinterpret_cast<uintptr_t>(x_bf16) | reinterpret_cast<uintptr_t>(out_bf16)) & 15)
+        return VITK_ERR_ARG;
+    ThGemmArgs a;
+    a.B = B; a.H = H; a.N = N; a.Np = Np;
+    const int variant = th_apply_variant();
+    a.HG = variant == 1 ? min(H, 256 / d) : min(H, 512 / d);
+    a.a_col0 = 0; a.b_col0 = x_col0;
+    a.out = out_bf16; a.ldo = ldo; a.o_col0 = o_col0; a.out_f32 = 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (variant == 1) {
+        if (d == 64) {
+            if (transpose) return launch_th_apply<64, true, 1>(p_bf16, x_bf16, ldx, x_cols, a, st);
+            return launch_th_apply<64, false, 1>(p_bf16, x_bf16, ldx, x_cols, a, st);
+        }
+        if (transpose) return launch_th_apply<48, true, 1>(p_bf16, x_bf16, ldx, x_cols, a, st);
+        return launch_th_apply<48, false, 1>(p_bf16, x_bf16, ldx, x_cols, a, st);
+    }
+    if (d == 64) {
+        if (transpose) return launch_th_apply<64, true, 2>(p_bf16, x_bf16, ldx, x_cols, a, st);
+        return launch_th_apply<64, false, 2>(p_bf16, x_bf16, ldx, x_cols, a, st);
+    }
+    if (transpose) return launch_th_apply<48, true, 2>(p_bf16, x_bf16, ldx, x_cols, a, st);
+    return launch_th_apply<48, false, 2>(p_bf16, x_bf16, ldx, x_cols, a, st);
+}

@@ -73,9 +73,30 @@ __device__ __forceinline__ void th2_c_to_a(const float (&c)[4], uint32_t (&a)[4]
 // ------------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------------
-template <int H, int NT>
+// logits of two adjacent key columns of one head: fp32 plane (8-byte load) or bf16 plane (4-byte load; bf16 values are
+// exact in tf32, so the 3xTF32 logit mix needs no low part of S)
+template <typename ST> __device__ __forceinline__ float2 th2_load_s2(const ST* p) {
+    if constexpr (sizeof(ST) == 4) {
+        return __ldg(reinterpret_cast<const float2*>(p));
+    } else {
+        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p));
+        return make_float2(bf16_lo(v), bf16_hi(v));
+    }
+}
+
+// the same pair kept in the registers it was loaded into (bf16 planes: one packed 32-bit register)
+template <typename ST> struct Th2Raw { using type = float2; };
+template <> struct Th2Raw<__nv_bfloat16> { using type = uint32_t; };
+template <typename ST> __device__ __forceinline__ typename Th2Raw<ST>::type th2_load_raw(const ST* p) {
+    if constexpr (sizeof(ST) == 4) return __ldg(reinterpret_cast<const float2*>(p));
+    else return __ldg(reinterpret_cast<const uint32_t*>(p));
+}
+__device__ __forceinline__ float2 th2_raw_f2(float2 v) { return v; }
+__device__ __forceinline__ float2 th2_raw_f2(uint32_t v) { return make_float2(bf16_lo(v), bf16_hi(v)); }
+
+template <int H, int NT, typename ST>
 __global__ void __launch_bounds__(TH2_WARPS * 32)
-th_mix2_fwd_kernel(const float* __restrict__ S, const float* __restrict__ wl, const float* __restrict__ bl,
+th_mix2_fwd_kernel(const ST* __restrict__ S, const float* __restrict__ wl, const float* __restrict__ bl,
                    const float* __restrict__ ww, const float* __restrict__ bw, float scale,
                    __nv_bfloat16* __restrict__ Pm, float* __restrict__ rowmax, float* __restrict__ rowsum, int B, int N,
                    int Np) {
@@ -111,7 +132,7 @@ th_mix2_fwd_kernel(const float* __restrict__ S, const float* __restrict__ wl, co
     const long long rows = (long long)B * N;
     for (long long row = (long long)blockIdx.x * TH2_WARPS + warp; row < rows; row += (long long)gridDim.x * TH2_WARPS) {
         const int b = static_cast<int>(row / N), i = static_cast<int>(row - (long long)b * N);
-        const float* Srow = S + ((long long)b * H * N + i) * Np;
+        const ST* Srow = S + ((long long)b * H * N + i) * Np;
         // all loads of the row go out first (NT tiles x 2 x KS 8-byte loads per lane in flight): the row is one long
         // dependent chain otherwise and the kernel would run at one HBM round trip per tile
         float2 raw[NT][KS][2];
@@ -121,10 +142,8 @@ th_mix2_fwd_kernel(const float* __restrict__ S, const float* __restrict__ wl, co
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 const int h0 = 8 * ks + tig, h1 = h0 + 4;
-                raw[t][ks][0] = (col < Np && h0 < H) ? __ldg(reinterpret_cast<const float2*>(Srow + h0 * plane + col))
-                                                     : make_float2(0.f, 0.f);
-                raw[t][ks][1] = (col < Np && h1 < H) ? __ldg(reinterpret_cast<const float2*>(Srow + h1 * plane + col))
-                                                     : make_float2(0.f, 0.f);
+                raw[t][ks][0] = (col < Np && h0 < H) ? th2_load_s2(Srow + h0 * plane + col) : make_float2(0.f, 0.f);
+                raw[t][ks][1] = (col < Np && h1 < H) ? th2_load_s2(Srow + h1 * plane + col) : make_float2(0.f, 0.f);
             }
         }
         float sp[NT][KS][4];   // mixed logits (log2 domain), C layout
@@ -148,7 +167,7 @@ th_mix2_fwd_kernel(const float* __restrict__ S, const float* __restrict__ wl, co
                     float d[4] = {bl2[nt][0], bl2[nt][1], bl2[nt][0], bl2[nt][1]};
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks) {
-                        mma_tf32(d, al[ks], b1h[ks][nt]);
+                        if constexpr (sizeof(ST) == 4) mma_tf32(d, al[ks], b1h[ks][nt]);
                         mma_tf32(d, ah[ks], b1l[ks][nt]);
                         mma_tf32(d, ah[ks], b1h[ks][nt]);
                     }
@@ -242,15 +261,21 @@ template <int H> struct Th2Scratch {
     static constexpr int FLOATS = 4 * ARR;                        // dP' | dS' | P | S
 };
 
-template <int H, int NT>
-__global__ void __launch_bounds__(TH2_WARPS * 32, 1)
-th_mix2_bwd_kernel(const float* __restrict__ S, const __nv_bfloat16* __restrict__ dPm, const float* __restrict__ rowmax,
+// bf16 logit planes run the LEAN form: the row stays in the (packed) registers it was loaded into and phase 2 recomputes
+// P and dP of a tile with three more mma.sync instead of keeping 8 fp32 per tile per lane alive across the row -- half
+// the registers, two thread blocks per SM (the kernel is bound by the latency of its dependent mma / exp chains, not by
+// the tensor pipe: 8 clk per mma.sync per SM sub-partition, scripts/micro/pipe_rates.cu).
+// Variants (WARPS per block, MINB blocks per SM, LEAN): (8, 1, false) the original; (8, 2, true) 128 registers; (12, 1,
+// true) 168 registers. VITK_TH_BWD picks one at run time (cait_attn.cu) for A/B runs.
+template <int H, int NT, typename ST, int WARPS, int MINB, bool LEAN_>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+th_mix2_bwd_kernel(const ST* __restrict__ S, const __nv_bfloat16* __restrict__ dPm, const float* __restrict__ rowmax,
                    const float* __restrict__ rowsum, const float* __restrict__ wl, const float* __restrict__ bl,
                    const float* __restrict__ ww, float scale, __nv_bfloat16* __restrict__ dS, float* __restrict__ dwl,
                    float* __restrict__ dbl, float* __restrict__ dww, float* __restrict__ dbw, int B, int N, int Np) {
     constexpr int KS = Th2<H>::KS;
     constexpr int HS = Th2Scratch<H>::HS, ARR = Th2Scratch<H>::ARR;
-    __shared__ __align__(16) float scratch_all[TH2_WARPS][Th2Scratch<H>::FLOATS];
+    __shared__ __align__(16) float scratch_all[WARPS][Th2Scratch<H>::FLOATS];
     __shared__ float red[2 * H * H + 2 * H];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = lane >> 2, tig = lane & 3;
@@ -297,7 +322,7 @@ th_mix2_bwd_kernel(const float* __restrict__ S, const __nv_bfloat16* __restrict_
     for (int ks = 0; ks < KS; ++ks) acc_dbw[ks][0] = acc_dbw[ks][1] = acc_dbl[ks][0] = acc_dbl[ks][1] = 0.f;
 
     const long long rows = (long long)B * N;
-    for (long long row = (long long)blockIdx.x * TH2_WARPS + warp; row < rows; row += (long long)gridDim.x * TH2_WARPS) {
+    for (long long row = (long long)blockIdx.x * WARPS + warp; row < rows; row += (long long)gridDim.x * WARPS) {
         const int b = static_cast<int>(row / N), i = static_cast<int>(row - (long long)b * N);
         const long long base = ((long long)b * H * N + i) * Np;
         float m2[KS][2], inv[KS][2];
@@ -310,7 +335,9 @@ th_mix2_bwd_kernel(const float* __restrict__ S, const __nv_bfloat16* __restrict_
                 inv[nt][e] = g < H ? 1.0f / rowsum[((long long)b * H + g) * N + i] : 0.f;
             }
         // all loads of the row first (see the forward kernel)
-        float2 rs[NT][KS][2];
+        using RawS = typename Th2Raw<ST>::type;
+        constexpr bool LEAN = LEAN_;
+        RawS rs[NT][KS][2];
         uint32_t rd[NT][KS][2];
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
@@ -319,25 +346,74 @@ th_mix2_bwd_kernel(const float* __restrict__ S, const __nv_bfloat16* __restrict_
             for (int ks = 0; ks < KS; ++ks) {
                 const int h0 = 8 * ks + tig, h1 = h0 + 4;
                 const bool ok0 = col < Np && h0 < H, ok1 = col < Np && h1 < H;
-                rs[t][ks][0] = ok0 ? __ldg(reinterpret_cast<const float2*>(S + base + h0 * plane + col)) : make_float2(0.f, 0.f);
-                rs[t][ks][1] = ok1 ? __ldg(reinterpret_cast<const float2*>(S + base + h1 * plane + col)) : make_float2(0.f, 0.f);
+                rs[t][ks][0] = ok0 ? th2_load_raw(S + base + h0 * plane + col) : RawS();
+                rs[t][ks][1] = ok1 ? th2_load_raw(S + base + h1 * plane + col) : RawS();
                 rd[t][ks][0] = ok0 ? __ldg(reinterpret_cast<const uint32_t*>(dPm + base + h0 * plane + col)) : 0u;
                 rd[t][ks][1] = ok1 ? __ldg(reinterpret_cast<const uint32_t*>(dPm + base + h1 * plane + col)) : 0u;
             }
         }
-        float P[NT][KS][4], dP[NT][KS][4];
+        float P[LEAN ? 1 : NT][KS][4], dP[LEAN ? 1 : NT][KS][4];
         float rp[KS][2];
 #pragma unroll
         for (int nt = 0; nt < KS; ++nt) rp[nt][0] = rp[nt][1] = 0.f;
+        // P and dP of tile t (C layout) from the row registers
+        auto tile_pd = [&](int t, float (&pt)[KS][4], float (&qt)[KS][4]) {
+            const int col = t * 16 + 2 * gid;
+            uint32_t ah[KS][4], al[KS][4], ad[KS][4];
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const float2 v0 = th2_raw_f2(rs[t][ks][0]), v1 = th2_raw_f2(rs[t][ks][1]);
+                if constexpr (sizeof(ST) == 4) {
+                    split_tf32(v0.x, ah[ks][0], al[ks][0]);
+                    split_tf32(v0.y, ah[ks][1], al[ks][1]);
+                    split_tf32(v1.x, ah[ks][2], al[ks][2]);
+                    split_tf32(v1.y, ah[ks][3], al[ks][3]);
+                } else {    // bf16 values are tf32 values: no rounding, no low part
+                    ah[ks][0] = __float_as_uint(v0.x); ah[ks][1] = __float_as_uint(v0.y);
+                    ah[ks][2] = __float_as_uint(v1.x); ah[ks][3] = __float_as_uint(v1.y);
+                    al[ks][0] = al[ks][1] = al[ks][2] = al[ks][3] = 0u;
+                }
+                const uint32_t d0 = rd[t][ks][0], d1 = rd[t][ks][1];
+                ad[ks][0] = col < N ? (d0 << 16) : 0u;
+                ad[ks][1] = col + 1 < N ? (d0 & 0xffff0000u) : 0u;
+                ad[ks][2] = col < N ? (d1 << 16) : 0u;
+                ad[ks][3] = col + 1 < N ? (d1 & 0xffff0000u) : 0u;
+            }
+#pragma unroll
+            for (int nt = 0; nt < KS; ++nt) {
+                float d[4] = {bl2[nt][0], bl2[nt][1], bl2[nt][0], bl2[nt][1]};
+                float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    if constexpr (sizeof(ST) == 4) mma_tf32(d, al[ks], b1h[ks][nt]);
+                    mma_tf32(d, ah[ks], b1l[ks][nt]);
+                    mma_tf32(d, ah[ks], b1h[ks][nt]);
+                    mma_tf32(q, ad[ks], bdp[ks][nt]);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool valid = (col + (e >> 1)) < N;
+                    pt[nt][e] = valid ? ex2_approx(d[e] - m2[nt][e & 1]) * inv[nt][e & 1] : 0.f;
+                    qt[nt][e] = q[e];
+                }
+            }
+        };
         // ---- phase 1: P, dP and rowsum(dP o P)
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            {
+            if constexpr (LEAN) {
+                float pt[KS][4], qt[KS][4];
+                tile_pd(t, pt, qt);
+#pragma unroll
+                for (int nt = 0; nt < KS; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) rp[nt][e & 1] = fmaf(pt[nt][e], qt[nt][e], rp[nt][e & 1]);
+            } else {
                 const int col = t * 16 + 2 * gid;
                 uint32_t ah[KS][4], al[KS][4], ad[KS][4];
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
-                    const float2 v0 = rs[t][ks][0], v1 = rs[t][ks][1];
+                    const float2 v0 = th2_raw_f2(rs[t][ks][0]), v1 = th2_raw_f2(rs[t][ks][1]);
                     split_tf32(v0.x, ah[ks][0], al[ks][0]);
                     split_tf32(v0.y, ah[ks][1], al[ks][1]);
                     split_tf32(v1.x, ah[ks][2], al[ks][2]);
@@ -356,7 +432,7 @@ th_mix2_bwd_kernel(const float* __restrict__ S, const __nv_bfloat16* __restrict_
                     float q[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks) {
-                        mma_tf32(d, al[ks], b1h[ks][nt]);
+                        if constexpr (sizeof(ST) == 4) mma_tf32(d, al[ks], b1h[ks][nt]);
                         mma_tf32(d, ah[ks], b1l[ks][nt]);
                         mma_tf32(d, ah[ks], b1h[ks][nt]);
                         mma_tf32(q, ad[ks], bdp[ks][nt]);
@@ -382,6 +458,19 @@ th_mix2_bwd_kernel(const float* __restrict__ S, const __nv_bfloat16* __restrict_
                 r += __shfl_xor_sync(0xffffffffu, r, 16);
                 rp[nt][e] = r;
             }
+        if constexpr (LEAN) {
+            // phase 2 recomputes from the row registers: keep the compiler from carrying phase 1's operand fragments
+            // across the row instead (that would be the register footprint this form exists to avoid)
+#pragma unroll
+            for (int t = 0; t < NT; ++t)
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        asm volatile("" : "+r"(rd[t][ks][e]));
+                        if constexpr (sizeof(RawS) == 4) asm volatile("" : "+r"(*reinterpret_cast<uint32_t*>(&rs[t][ks][e])));
+                    }
+        }
         // ---- phase 2: dS', dS, weight gradients
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
@@ -390,10 +479,22 @@ th_mix2_bwd_kernel(const float* __restrict__ S, const __nv_bfloat16* __restrict_
                 const bool inb = col < Np;
                 float dsp[KS][4];
                 uint32_t a[KS][4];
+                float pt[KS][4], qt[KS][4];
+                if constexpr (LEAN) {
+                    tile_pd(t, pt, qt);
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            pt[ks][e] = P[t][ks][e];
+                            qt[ks][e] = dP[t][ks][e];
+                        }
+                }
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) dsp[ks][e] = P[t][ks][e] * (dP[t][ks][e] - rp[ks][e & 1]);
+                    for (int e = 0; e < 4; ++e) dsp[ks][e] = pt[ks][e] * (qt[ks][e] - rp[ks][e & 1]);
                     th2_c_to_a(dsp[ks], a[ks]);
                     acc_dbl[ks][0] += dsp[ks][0] + dsp[ks][2];
                     acc_dbl[ks][1] += dsp[ks][1] + dsp[ks][3];
@@ -417,7 +518,7 @@ th_mix2_bwd_kernel(const float* __restrict__ S, const __nv_bfloat16* __restrict_
                 for (int ks = 0; ks < KS; ++ks) {
                     const int h0 = 8 * ks + tig, h1 = h0 + 4;
                     // S and dP' in A layout: still in the registers the row was loaded into
-                    const float2 s0 = rs[t][ks][0], s1 = rs[t][ks][1];
+                    const float2 s0 = th2_raw_f2(rs[t][ks][0]), s1 = th2_raw_f2(rs[t][ks][1]);
                     const uint32_t d0 = rd[t][ks][0], d1 = rd[t][ks][1];
                     const float2 e0 = make_float2(col < N ? bf16_lo(d0) : 0.f, col + 1 < N ? bf16_hi(d0) : 0.f);
                     const float2 e1 = make_float2(col < N ? bf16_lo(d1) : 0.f, col + 1 < N ? bf16_hi(d1) : 0.f);
@@ -430,8 +531,8 @@ th_mix2_bwd_kernel(const float* __restrict__ S, const __nv_bfloat16* __restrict_
                     *reinterpret_cast<float2*>(sc_dpm + h0 * HS + 2 * gid) = e0;
                     *reinterpret_cast<float2*>(sc_dpm + h1 * HS + 2 * gid) = e1;
                     const int g0 = 8 * ks + 2 * tig;   // C layout: heads g0, g0+1
-                    *reinterpret_cast<float2*>(sc_p + g0 * HS + 2 * gid) = make_float2(P[t][ks][0], P[t][ks][2]);
-                    *reinterpret_cast<float2*>(sc_p + (g0 + 1) * HS + 2 * gid) = make_float2(P[t][ks][1], P[t][ks][3]);
+                    *reinterpret_cast<float2*>(sc_p + g0 * HS + 2 * gid) = make_float2(pt[ks][0], pt[ks][2]);
+                    *reinterpret_cast<float2*>(sc_p + (g0 + 1) * HS + 2 * gid) = make_float2(pt[ks][1], pt[ks][3]);
                     *reinterpret_cast<float2*>(sc_dsp + g0 * HS + 2 * gid) = make_float2(dsp[ks][0], dsp[ks][2]);
                     *reinterpret_cast<float2*>(sc_dsp + (g0 + 1) * HS + 2 * gid) = make_float2(dsp[ks][1], dsp[ks][3]);
                 }

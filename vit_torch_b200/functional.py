@@ -99,6 +99,12 @@ def _flat_grads(params, needs, device):
     return buf, views
 
 
+def _th_s_f32() -> bool:
+    """Talking-heads logit planes in fp32 instead of bf16 (VITK_TH_S_F32=1; twice the plane traffic)."""
+    import os
+    return os.environ.get("VITK_TH_S_F32", "0") == "1"
+
+
 def _dy_bf16(dy2d, M, D, gamma=None, rowscale=None, rows_per_sample=0):
     """bf16 copy of an fp32 residual-stream gradient (scaled by LayerScale gamma / DropPath), reusing the copy the
     producing kernel already wrote when there is one."""
@@ -138,13 +144,20 @@ class BlockFn(torch.autograd.Function):
             # talking-heads attention (models/cait.py:111-128): raw logits by a batched tcgen05 GEMM reading q/k in
             # place, one fused mixing/softmax/mixing pass, P'.V by a second batched GEMM
             Np = (N + 7) // 8 * 8
-            S = torch.empty((B, H, N, Np), dtype=torch.float32, device=dev)
-            ops.gemm_batched(qkv, 3 * D, d, N * 3 * D, False, qkv, 3 * D, d, N * 3 * D, False, N, N, d, H, B, S, Np,
-                             N * Np, H * N * Np, a_off=0, b_off=D, out_f32=True)
-            Pm, rmax, rsum = ops.th_mix_fwd(S, thl_w, thl_b, thw_w, thw_b, scale, B, H, N, Np)
             o = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
-            ops.gemm_batched(Pm, Np, N * Np, H * N * Np, False, qkv, 3 * D, d, N * 3 * D, True, N, d, N, H, B, o, D, d,
-                             N * D, b_off=2 * D)
+            if ops.th_gemm_ok(N, d, Np):
+                # short sequences (CaiT at 224 px): whole-image products, one thread block per (image, row block)
+                # walking the heads; the logit planes are bf16 as under torch.autocast (VITK_TH_S_F32=1: fp32)
+                S = ops.th_scores(qkv, 0, qkv, D, B, N, H, d, Np, out_f32=_th_s_f32())
+                Pm, rmax, rsum = ops.th_mix_fwd(S, thl_w, thl_b, thw_w, thw_b, scale, B, H, N, Np)
+                ops.th_apply(Pm, qkv, 2 * D, o, 0, B, N, H, d, Np)
+            else:
+                S = torch.empty((B, H, N, Np), dtype=torch.float32, device=dev)
+                ops.gemm_batched(qkv, 3 * D, d, N * 3 * D, False, qkv, 3 * D, d, N * 3 * D, False, N, N, d, H, B, S, Np,
+                                 N * Np, H * N * Np, a_off=0, b_off=D, out_f32=True)
+                Pm, rmax, rsum = ops.th_mix_fwd(S, thl_w, thl_b, thw_w, thw_b, scale, B, H, N, Np)
+                ops.gemm_batched(Pm, Np, N * Np, H * N * Np, False, qkv, 3 * D, d, N * 3 * D, True, N, d, N, H, B, o, D,
+                                 d, N * D, b_off=2 * D)
             if not need_bwd:
                 S = Pm = None
         x1 = torch.empty((M, D), dtype=torch.float32, device=dev)
@@ -245,21 +258,31 @@ class BlockFn(torch.autograd.Function):
             dthl_b = dthl_b if dthl_b is not None else zeros(thl_b)
             dthw_w = dthw_w if dthw_w is not None else zeros(thw_w)
             dthw_b = dthw_b if dthw_b is not None else zeros(thw_b)
-            dp16 = ops.th_mix_bf16_dp(Np)       # version-2 mixing kernels read dP' in bf16
-            dPm = torch.empty((B, H, N, Np), dtype=torch.bfloat16 if dp16 else torch.float32, device=dev)
-            ops.gemm_batched(do, D, d, N * D, False, qkv, 3 * D, d, N * 3 * D, False, N, N, d, H, B, dPm, Np, N * Np,
-                             H * N * Np, b_off=2 * D, out_f32=not dp16)     # dP'[i,j] = dO_i . v_j
             dqkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
-            ops.gemm_batched(Pm, Np, N * Np, H * N * Np, True, do, D, d, N * D, True, N, d, N, H, B, dqkv, 3 * D, d,
-                             N * 3 * D, out_off=2 * D)                              # dV = P'^T dO
-            dS = ops.th_mix_bwd(S, dPm, rmax, rsum, thl_w, thl_b, thw_w, thw_b, scale, dthl_w, dthl_b, dthw_w, dthw_b,
-                                B, H, N, Np)
-            del dPm
-            ops.gemm_batched(dS, Np, N * Np, H * N * Np, False, qkv, 3 * D, d, N * 3 * D, True, N, d, N, H, B, dqkv,
-                             3 * D, d, N * 3 * D, b_off=D, out_off=0)               # dQ = dS K
-            ops.gemm_batched(dS, Np, N * Np, H * N * Np, True, qkv, 3 * D, d, N * 3 * D, True, N, d, N, H, B, dqkv,
-                             3 * D, d, N * 3 * D, b_off=0, out_off=D)               # dK = dS^T Q
-            del dS
+            if ops.th_gemm_ok(N, d, Np) and (S.dtype == torch.bfloat16 or ops.th_mix_bf16_dp(Np)):
+                dPm = ops.th_scores(do, 0, qkv, 2 * D, B, N, H, d, Np)                  # dP'[i,j] = dO_i . v_j (bf16)
+                ops.th_apply_t(Pm, do, 0, dqkv, 2 * D, B, N, H, d, Np)    # dV = P'^T dO
+                dS = ops.th_mix_bwd(S, dPm, rmax, rsum, thl_w, thl_b, thw_w, thw_b, scale, dthl_w, dthl_b, dthw_w,
+                                    dthw_b, B, H, N, Np)
+                del dPm
+                ops.th_apply(dS, qkv, D, dqkv, 0, B, N, H, d, Np)                       # dQ = dS K
+                ops.th_apply_t(dS, qkv, 0, dqkv, D, B, N, H, d, Np)       # dK = dS^T Q
+                del dS
+            else:
+                dp16 = ops.th_mix_bf16_dp(Np)       # version-2 mixing kernels read dP' in bf16
+                dPm = torch.empty((B, H, N, Np), dtype=torch.bfloat16 if dp16 else torch.float32, device=dev)
+                ops.gemm_batched(do, D, d, N * D, False, qkv, 3 * D, d, N * 3 * D, False, N, N, d, H, B, dPm, Np, N * Np,
+                                 H * N * Np, b_off=2 * D, out_f32=not dp16)     # dP'[i,j] = dO_i . v_j
+                ops.gemm_batched(Pm, Np, N * Np, H * N * Np, True, do, D, d, N * D, True, N, d, N, H, B, dqkv, 3 * D, d,
+                                 N * 3 * D, out_off=2 * D)                              # dV = P'^T dO
+                dS = ops.th_mix_bwd(S, dPm, rmax, rsum, thl_w, thl_b, thw_w, thw_b, scale, dthl_w, dthl_b, dthw_w,
+                                    dthw_b, B, H, N, Np)
+                del dPm
+                ops.gemm_batched(dS, Np, N * Np, H * N * Np, False, qkv, 3 * D, d, N * 3 * D, True, N, d, N, H, B, dqkv,
+                                 3 * D, d, N * 3 * D, b_off=D, out_off=0)               # dQ = dS K
+                ops.gemm_batched(dS, Np, N * Np, H * N * Np, True, qkv, 3 * D, d, N * 3 * D, True, N, d, N, H, B, dqkv,
+                                 3 * D, d, N * 3 * D, b_off=0, out_off=D)               # dK = dS^T Q
+                del dS
             if not needs[19]: dthl_w = None
             if not needs[20]: dthl_b = None
             if not needs[21]: dthw_w = None

@@ -5,6 +5,8 @@ if the library is missing or the tensors are not CUDA tensors -- there is no eag
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -386,16 +388,56 @@ def gemm_batched(a, lda, sa_h, sa_b, a_mn, b, ldb, sb_h, sb_b, b_mn, M, N, K, nh
     return out
 
 
+def th_gemm_ok(N, d, Np) -> bool:
+    """True when the short-sequence talking-heads products (th_scores / th_apply) serve this shape.
+    VITK_TH_GEMM=0 keeps the generic batched GEMM (A/B runs)."""
+    if os.environ.get("VITK_TH_GEMM", "1") == "0":
+        return False
+    return bool(_lib.load().vitk_th_gemm_supported(int(N), int(d), int(Np)))
+
+
+def th_scores(a, a_col0, b, b_col0, B, N, H, d, Np, out_f32=False):
+    """out[b,h,i,j] = a_h[i] . b_h[j] over token-major bf16 matrices a, b ([B*N, cols], head h = columns col0 + h*d ..).
+    -> plane [B,H,N,Np], bf16 (the dtype torch.autocast gives the reference's q @ k^T) or fp32."""
+    global launch_count
+    _need_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    out = torch.empty((B, H, N, Np), dtype=torch.float32 if out_f32 else torch.bfloat16, device=a.device)
+    check(_lib.load().vitk_th_scores(ptr(a), a.stride(0), a.shape[1], a_col0, ptr(b), b.stride(0), b.shape[1], b_col0,
+                                     ptr(out), int(out_f32), B, N, H, d, Np, _stream()), "vitk_th_scores")
+    launch_count += 1
+    return out
+
+
+def th_apply(p, x, x_col0, out, o_col0, B, N, H, d, Np, transpose=False):
+    """out[b*N+i, o_col0+h*d+e] = sum_j p[b,h,i,j] x[b*N+j, x_col0+h*d+e]  (transpose: sum over i of p[b,h,i,j] x[b*N+i, ..]
+    into row j). p: bf16 plane [B,H,N,Np] with zero pad columns; x, out: token-major bf16."""
+    global launch_count
+    _need_cuda(p, x, out)
+    assert p.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+    check(_lib.load().vitk_th_apply(ptr(p), ptr(x), x.stride(0), x.shape[1], x_col0, ptr(out), out.stride(0), o_col0,
+                                    int(transpose), B, N, H, d, Np, _stream()), "vitk_th_apply")
+    launch_count += 1
+    return out
+
+
+def th_apply_t(p, x, x_col0, out, o_col0, B, N, H, d, Np):
+    """th_apply with the plane transposed: out[b*N+j] = sum_i p[b,h,i,j] x[b*N+i]."""
+    return _th_apply_impl(p, x, x_col0, out, o_col0, B, N, H, d, Np, transpose=True)
+
+
 def th_mix_fwd(S, wl, bl, ww, bw, scale, B, H, N, Np):
-    """Talking-heads mixing forward. S fp32 [B,H,N,Np] -> (Pm bf16 [B,H,N,Np], rowmax, rowsum fp32 [B,H,N])."""
+    """Talking-heads mixing forward. S fp32 or bf16 [B,H,N,Np] -> (Pm bf16 [B,H,N,Np], rowmax, rowsum fp32 [B,H,N])."""
     global launch_count
     _need_cuda(S, wl, bl, ww, bw)
     Pm = torch.empty((B, H, N, Np), dtype=torch.bfloat16, device=S.device)
     rmax = torch.empty((B, H, N), dtype=torch.float32, device=S.device)
     rsum = torch.empty((B, H, N), dtype=torch.float32, device=S.device)
     lib = _lib.load()
-    check(lib.vitk_th_mix_fwd(ptr(S), ptr(wl), ptr(bl), ptr(ww), ptr(bw), scale, ptr(Pm), ptr(rmax), ptr(rsum), B, H, N,
-                              Np, _stream()), "vitk_th_mix_fwd")
+    fn, name = ((lib.vitk_th_mix_fwd_s16, "vitk_th_mix_fwd_s16") if S.dtype == torch.bfloat16
+                else (lib.vitk_th_mix_fwd, "vitk_th_mix_fwd"))
+    check(fn(ptr(S), ptr(wl), ptr(bl), ptr(ww), ptr(bw), scale, ptr(Pm), ptr(rmax), ptr(rsum), B, H, N, Np, _stream()),
+          name)
     launch_count += 1
     return Pm, rmax, rsum
 
@@ -412,6 +454,13 @@ def th_mix_bwd(S, dPm, rmax, rsum, wl, bl, ww, bw, scale, dwl, dbl, dww, dbw, B,
     _need_cuda(S, dPm)
     dS = torch.empty((B, H, N, Np), dtype=torch.bfloat16, device=S.device)
     lib = _lib.load()
+    if S.dtype == torch.bfloat16:
+        assert dPm.dtype == torch.bfloat16
+        check(lib.vitk_th_mix_bwd_s16(ptr(S), ptr(dPm), ptr(rmax), ptr(rsum), ptr(wl), ptr(bl), ptr(ww), ptr(bw), scale,
+                                      ptr(dS), ptr(dwl), ptr(dbl), ptr(dww), ptr(dbw), B, H, N, Np, _stream()),
+              "vitk_th_mix_bwd_s16")
+        launch_count += 1
+        return dS
     if dPm.dtype == torch.bfloat16:
         check(lib.vitk_th_mix_bwd_bf16(ptr(S), ptr(dPm), ptr(rmax), ptr(rsum), ptr(wl), ptr(bl), ptr(ww), ptr(bw), scale,
                                        ptr(dS), ptr(dwl), ptr(dbl), ptr(dww), ptr(dbw), B, H, N, Np, _stream()),
@@ -490,8 +539,11 @@ def _timed(fn):
 
 for _name in ("gemm", "gemm_batched", "layernorm_fwd", "layernorm_bwd", "layernorm_fwd_rows", "layernorm_bwd_rows",
               "colsum_accum", "colsum_f32_accum", "colsum_prod_accum", "layerscale_bwd", "cast_bf16", "attn_fwd", "attn_bwd", "scale_cast",
-              "patchify", "prefix_tokens", "patch_embed_fwd", "patch_embed_wgrad", "normalize_u8", "th_mix_fwd", "th_mix_bwd", "class_attn_fwd", "class_attn_bwd"):
+              "patchify", "prefix_tokens", "patch_embed_fwd", "patch_embed_wgrad", "normalize_u8", "th_mix_fwd", "th_mix_bwd", "class_attn_fwd", "class_attn_bwd",
+              "th_scores", "th_apply_t"):
     globals()[_name] = _timed(globals()[_name])
+_th_apply_impl = th_apply
+th_apply = _timed(th_apply)          # (th_apply_t calls the untimed implementation: one event pair per launch)
 
 
 def sgd_momentum_multi(table, chunk_map, num_chunks, lr, momentum, grad_scale=1.0, first_step=False):
