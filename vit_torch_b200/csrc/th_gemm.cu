@@ -42,12 +42,14 @@ struct ThGemmArgs {
 // [128 x 208] fp32 in TMEM (256 columns allocated: two thread blocks per SM).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int TS_STAGE = TG_T128 + TG_TIMG;                 // 43008
-constexpr int TS_SMEM_BAR = TG_NS * TS_STAGE;
+constexpr int TS_SMEM_OUT = TG_NS * TS_STAGE;               // [128 x 64] bf16 staging tile of the TMA store
+constexpr int TS_SMEM_BAR = TS_SMEM_OUT + TG_T128;
 constexpr int TS_SMEM_BYTES = TS_SMEM_BAR + 128;
 
 template <int HD>
 __global__ void __launch_bounds__(TG_THREADS, 2)
-th_scores_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ThGemmArgs a) {
+th_scores_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const ThGemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TS_SMEM_BAR);
     uint64_t* full = bars;               // [TG_NS]
@@ -118,6 +120,54 @@ th_scores_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int c_begin = half ? 112 : 0, c_end = half ? TG_ROWS : 112;
         const int esz = a.out_f32 ? 4 : 2;
         int it = 0;
+        if (!a.out_f32) {
+            // bf16 planes leave as [128 rows x 64 columns] tiles: the eight warps transpose their TMEM slabs into one
+            // swizzled staging tile and ONE TMA store writes it (rows >= N and columns >= Np are clipped by the map).
+            // Per-lane stores of a row-per-lane TMEM slab would touch 32 different 128-byte lines per instruction -- the
+            // first version of this kernel was bound by exactly that (50 us for an 80 MB plane).
+            uint8_t* stg = smem + TS_SMEM_OUT;
+            const int r = q * 32 + lane;                       // row inside the tile
+            uint8_t* stg_row = stg + r * 128;
+            const int sw = r & 7;
+            const int nchunk = (min(nk16, a.Np) + 63) >> 6;
+            for (int h = h0; h < h1; ++h, ++it) {
+                mbar_wait(acc_full, it & 1);
+                tc_fence_after_sync();
+                for (int c = 0; c < nchunk; ++c) {
+                    const int col0 = 64 * c + 32 * half;
+                    const bool active = col0 < nk16;           // (warp-uniform)
+                    uint32_t v[32];
+                    if (active) {
+                        tmem_ld_32x32b_x32(tmem_base + lane_off + col0, v);
+                        tmem_ld_wait();
+                    }
+                    if (c == nchunk - 1) {                     // all TMEM reads of this head are done
+                        tc_fence_before_sync();
+                        mbar_arrive(acc_free);
+                    }
+                    // the previous store out of the staging tile has finished reading it
+                    if (threadIdx.x == 0) tma_store_wait_read<0>();
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                        if (active)
+                            pk = make_uint4(pack_bf16(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
+                                            pack_bf16(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
+                                            pack_bf16(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
+                                            pack_bf16(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7])));
+                        *reinterpret_cast<uint4*>(stg_row + (((4 * half + u) ^ sw) << 4)) = pk;
+                    }
+                    fence_proxy_async_smem();
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (threadIdx.x == 0) {
+                        tma_store_3d(&tmO, stg, 64 * c, q0, b * a.H + h);
+                        tma_store_commit();
+                    }
+                }
+            }
+            if (threadIdx.x == 0) tma_store_wait<0>();
+        } else
         for (int h = h0; h < h1; ++h, ++it) {
             mbar_wait(acc_full, it & 1);
             tc_fence_after_sync();
@@ -326,6 +376,11 @@ static int launch_th_scores(const void* A, long long lda, int a_cols, const void
     if (make_tmap_3d_rows(&tmA, A, (uint64_t)a_cols, (uint64_t)a.N, (uint64_t)a.B, (uint64_t)lda, (uint64_t)lda * a.N, 128) ||
         make_tmap_3d_rows(&tmB, Bm, (uint64_t)b_cols, (uint64_t)a.N, (uint64_t)a.B, (uint64_t)ldb, (uint64_t)ldb * a.N, TG_ROWS))
         return VITK_ERR_TMAP;
+    CUtensorMap tmO;
+    memset(&tmO, 0, sizeof(tmO));
+    if (!a.out_f32 && make_tmap_3d_rows(&tmO, a.out, (uint64_t)a.Np, (uint64_t)a.N, (uint64_t)a.B * a.H, (uint64_t)a.Np,
+                                        (uint64_t)a.Np * a.N, 128))
+        return VITK_ERR_TMAP;
     static bool attr = false;
     if (!attr) {
         if (cudaFuncSetAttribute(th_scores_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES) !=
@@ -334,7 +389,7 @@ static int launch_th_scores(const void* A, long long lda, int a_cols, const void
         attr = true;
     }
     dim3 grid((a.N + 127) / 128, (a.H + a.HG - 1) / a.HG, a.B);
-    th_scores_kernel<HD><<<grid, TG_THREADS, TS_SMEM_BYTES, st>>>(tmA, tmB, a);
+    th_scores_kernel<HD><<<grid, TG_THREADS, TS_SMEM_BYTES, st>>>(tmA, tmB, tmO, a);
     return cudaGetLastError() == cudaSuccess ? VITK_OK : VITK_ERR_CUDA;
 }
 

@@ -261,12 +261,12 @@ class BlockFn(torch.autograd.Function):
             dqkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
             if ops.th_gemm_ok(N, d, Np) and (S.dtype == torch.bfloat16 or ops.th_mix_bf16_dp(Np)):
                 dPm = ops.th_scores(do, 0, qkv, 2 * D, B, N, H, d, Np)                  # dP'[i,j] = dO_i . v_j (bf16)
-                ops.th_apply_t(Pm, do, 0, dqkv, 2 * D, B, N, H, d, Np)    # dV = P'^T dO
+                ops.th_apply_t(Pm, do, 0, dqkv, 2 * D, B, N, H, d, Np)                  # dV = P'^T dO
                 dS = ops.th_mix_bwd(S, dPm, rmax, rsum, thl_w, thl_b, thw_w, thw_b, scale, dthl_w, dthl_b, dthw_w,
                                     dthw_b, B, H, N, Np)
                 del dPm
                 ops.th_apply(dS, qkv, D, dqkv, 0, B, N, H, d, Np)                       # dQ = dS K
-                ops.th_apply_t(dS, qkv, 0, dqkv, D, B, N, H, d, Np)       # dK = dS^T Q
+                ops.th_apply_t(dS, qkv, 0, dqkv, D, B, N, H, d, Np)                     # dK = dS^T Q
                 del dS
             else:
                 dp16 = ops.th_mix_bf16_dp(Np)       # version-2 mixing kernels read dP' in bf16
