@@ -93,6 +93,7 @@ def family_work_per_image(w):
 
 OP_FAMILY = {"gemm": "gemm", "gemm_batched": "attention", "patch_embed_fwd": "gemm", "patch_embed_wgrad": "gemm",
              "attn_fwd": "attention", "attn_bwd": "attention", "th_mix_fwd": "attention", "th_mix_bwd": "attention",
+             "th_scores": "attention", "th_apply": "attention", "th_apply_t": "attention",
              "class_attn_fwd": "attention", "class_attn_bwd": "attention", "layernorm_fwd": "layernorm",
              "layernorm_bwd": "layernorm", "layernorm_fwd_rows": "layernorm", "layernorm_bwd_rows": "layernorm"}
 

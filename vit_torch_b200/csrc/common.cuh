@@ -213,6 +213,15 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
     while (!mbar_try_wait(bar, parity)) __nanosleep(32);
 }
 
+// The long waits of the GEMM kernels' single-thread roles (producer: a free smem stage; MMA issuer: a free accumulator).
+// In the epilogue-bound instantiations (GELU / GELU' / residual) the bare polling loops of these two warps were 16 % of
+// all warp instructions and shared their schedulers with two of the eight epilogue warps (ncu, profiles/r02_summary.md);
+// VITK_GEMM_DBG bit 16 restores the bare loop for A/B runs.
+__device__ __forceinline__ void mbar_wait_role(uint64_t* bar, uint32_t parity, int dbg) {
+    if (dbg & 16) mbar_wait(bar, parity);
+    else mbar_wait_backoff(bar, parity);
+}
+
 // generic-proxy writes to smem -> visible to the async proxy (TMA / UMMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

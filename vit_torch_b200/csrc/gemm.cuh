@@ -594,7 +594,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (!batched) {
                     // plain GEMM: rank-2 tensor maps (rank-4 boxes cost 20-45% on MN-major operands)
                     for (int kb = kb0; kb < kb1; ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_wait_role(&empty_bar[stage], phase ^ 1, g.dbg);
                         mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                         uint8_t* sa = smem_a + stage * Cfg::A_STAGE_BYTES;
                         uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
@@ -623,7 +623,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         tma_load_4d(dst, tm, &full_bar[stage], c0, lc[perm[0]], lc[perm[1]], lc[perm[2]]);
                     };
                     for (int kb = kb0; kb < kb1; ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_wait_role(&empty_bar[stage], phase ^ 1, g.dbg);
                         mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                         uint8_t* sa = smem_a + stage * Cfg::A_STAGE_BYTES;
                         uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
@@ -663,7 +663,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int split = rest % g.splits;
                 const int kb0 = split * g.kblocks_per_split;
                 const int kb1 = min(kb0 + g.kblocks_per_split, g.num_kblocks);
-                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                mbar_wait_role(&tempty_bar[as], aphase ^ 1, g.dbg);
                 tc_fence_after_sync();
                 const uint32_t tmem_d = tmem_base + as * BN;
                 for (int kb = kb0; kb < kb1; ++kb) {

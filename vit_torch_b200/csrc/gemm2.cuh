@@ -108,7 +108,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int kb0 = split * g.kblocks_per_split;
                 const int kb1 = min(kb0 + g.kblocks_per_split, g.num_kblocks);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_wait_role(&empty_bar[stage], phase ^ 1, g.dbg);
                     if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
                     uint8_t* sa = smem_a + stage * Cfg::A_STAGE_BYTES;
                     uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
@@ -146,7 +146,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 decode(u, m_unit, n_tile, split);
                 const int kb0 = split * g.kblocks_per_split;
                 const int kb1 = min(kb0 + g.kblocks_per_split, g.num_kblocks);
-                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                mbar_wait_role(&tempty_bar[as], aphase ^ 1, g.dbg);
                 tc_fence_after_sync();
                 const uint32_t tmem_d = tmem_base + as * BN;
                 for (int kb = kb0; kb < kb1; ++kb) {

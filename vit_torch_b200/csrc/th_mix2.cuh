@@ -94,6 +94,30 @@ template <typename ST> __device__ __forceinline__ typename Th2Raw<ST>::type th2_
 __device__ __forceinline__ float2 th2_raw_f2(float2 v) { return v; }
 __device__ __forceinline__ float2 th2_raw_f2(uint32_t v) { return make_float2(bf16_lo(v), bf16_hi(v)); }
 
+// Per-lane element offsets inside a (b, i) row group of the planes: heads in A layout (tig, tig+4: what the lane loads)
+// and in C layout (2tig, 2tig+1: what it stores), first column 2*gid of a tile. Tile t adds the constant 16*t, so the
+// unrolled row needs no address arithmetic per access (it was 18 % of the forward kernel's instructions).
+template <int H> struct Th2Off {
+    static constexpr int KS = Th2<H>::KS;
+    long long a[KS][2], c[KS][2];
+    bool a_ok[KS][2], c_ok[KS][2];
+    __device__ __forceinline__ Th2Off(long long plane, int gid, int tig) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int ha = 8 * ks + tig + 4 * e, hc = 8 * ks + 2 * tig + e;
+                a_ok[ks][e] = (H % 8 == 0) || ha < H;
+                c_ok[ks][e] = (H % 8 == 0) || hc < H;
+                a[ks][e] = (a_ok[ks][e] ? ha : 0) * plane + 2 * gid;
+                c[ks][e] = (c_ok[ks][e] ? hc : 0) * plane + 2 * gid;
+            }
+    }
+};
+
+struct Th2True { static constexpr bool value = true; };
+struct Th2False { static constexpr bool value = false; };
+
 template <int H, int NT, typename ST>
 __global__ void __launch_bounds__(TH2_WARPS * 32)
 th_mix2_fwd_kernel(const ST* __restrict__ S, const float* __restrict__ wl, const float* __restrict__ bl,
@@ -101,10 +125,13 @@ th_mix2_fwd_kernel(const ST* __restrict__ S, const float* __restrict__ wl, const
                    __nv_bfloat16* __restrict__ Pm, float* __restrict__ rowmax, float* __restrict__ rowsum, int B, int N,
                    int Np) {
     constexpr int KS = Th2<H>::KS;
+    using RawS = typename Th2Raw<ST>::type;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     const long long plane = (long long)N * Np;
     constexpr float kLog2e = 1.4426950408889634f;
+    const Th2Off<H> off(plane, gid, tig);
+    const int nfull = N >> 4;    // tiles whose 16 columns are all real keys: no masks, no bounds checks (N <= Np)
 
     // mixing matrices as B fragments (constant over the kernel). Logit mix in the log2 domain: scale*log2e folded in.
     uint32_t b1h[KS][KS][2], b1l[KS][KS][2], b2[KS][KS][2];
@@ -132,53 +159,73 @@ th_mix2_fwd_kernel(const ST* __restrict__ S, const float* __restrict__ wl, const
     const long long rows = (long long)B * N;
     for (long long row = (long long)blockIdx.x * TH2_WARPS + warp; row < rows; row += (long long)gridDim.x * TH2_WARPS) {
         const int b = static_cast<int>(row / N), i = static_cast<int>(row - (long long)b * N);
-        const ST* Srow = S + ((long long)b * H * N + i) * Np;
-        // all loads of the row go out first (NT tiles x 2 x KS 8-byte loads per lane in flight): the row is one long
+        const long long base = ((long long)b * H * N + i) * Np;
+        const ST* Srow = S + base;
+        // all loads of the row go out first (NT tiles x 2 x KS loads per lane in flight): the row is one long
         // dependent chain otherwise and the kernel would run at one HBM round trip per tile
-        float2 raw[NT][KS][2];
+        RawS raw[NT][KS][2];
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            const int col = t * 16 + 2 * gid;
+            if (t < nfull) {
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                const int h0 = 8 * ks + tig, h1 = h0 + 4;
-                raw[t][ks][0] = (col < Np && h0 < H) ? th2_load_s2(Srow + h0 * plane + col) : make_float2(0.f, 0.f);
-                raw[t][ks][1] = (col < Np && h1 < H) ? th2_load_s2(Srow + h1 * plane + col) : make_float2(0.f, 0.f);
+                for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        raw[t][ks][e] = off.a_ok[ks][e] ? th2_load_raw(Srow + off.a[ks][e] + t * 16) : RawS();
+            } else {
+                const bool inb = t * 16 + 2 * gid < Np;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        raw[t][ks][e] = (inb && off.a_ok[ks][e]) ? th2_load_raw(Srow + off.a[ks][e] + t * 16) : RawS();
             }
         }
         float sp[NT][KS][4];   // mixed logits (log2 domain), C layout
         float mx[KS][2];
 #pragma unroll
         for (int nt = 0; nt < KS; ++nt) mx[nt][0] = mx[nt][1] = -INFINITY;
+        auto logits_tile = [&](auto masked_c, int t) {
+            constexpr bool MASKED = decltype(masked_c)::value;
+            uint32_t ah[KS][4], al[KS][4];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            {
-                const int col = t * 16 + 2 * gid;
-                uint32_t ah[KS][4], al[KS][4];
-#pragma unroll
-                for (int ks = 0; ks < KS; ++ks) {
-                    split_tf32(raw[t][ks][0].x, ah[ks][0], al[ks][0]);
-                    split_tf32(raw[t][ks][0].y, ah[ks][1], al[ks][1]);
-                    split_tf32(raw[t][ks][1].x, ah[ks][2], al[ks][2]);
-                    split_tf32(raw[t][ks][1].y, ah[ks][3], al[ks][3]);
-                }
-#pragma unroll
-                for (int nt = 0; nt < KS; ++nt) {
-                    float d[4] = {bl2[nt][0], bl2[nt][1], bl2[nt][0], bl2[nt][1]};
-#pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) {
-                        if constexpr (sizeof(ST) == 4) mma_tf32(d, al[ks], b1h[ks][nt]);
-                        mma_tf32(d, ah[ks], b1l[ks][nt]);
-                        mma_tf32(d, ah[ks], b1h[ks][nt]);
-                    }
-                    if (col >= N) d[0] = d[1] = -INFINITY;          // columns 2gid / 2gid+1 of the tile
-                    if (col + 1 >= N) d[2] = d[3] = -INFINITY;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) sp[t][nt][e] = d[e];
-                    mx[nt][0] = fmaxf(mx[nt][0], fmaxf(d[0], d[2]));
-                    mx[nt][1] = fmaxf(mx[nt][1], fmaxf(d[1], d[3]));
+            for (int ks = 0; ks < KS; ++ks) {
+                const float2 v0 = th2_raw_f2(raw[t][ks][0]), v1 = th2_raw_f2(raw[t][ks][1]);
+                if constexpr (sizeof(ST) == 4) {
+                    split_tf32(v0.x, ah[ks][0], al[ks][0]);
+                    split_tf32(v0.y, ah[ks][1], al[ks][1]);
+                    split_tf32(v1.x, ah[ks][2], al[ks][2]);
+                    split_tf32(v1.y, ah[ks][3], al[ks][3]);
+                } else {    // bf16 values are tf32 values: no rounding, no low part
+                    ah[ks][0] = __float_as_uint(v0.x); ah[ks][1] = __float_as_uint(v0.y);
+                    ah[ks][2] = __float_as_uint(v1.x); ah[ks][3] = __float_as_uint(v1.y);
+                    al[ks][0] = al[ks][1] = al[ks][2] = al[ks][3] = 0u;
                 }
             }
+#pragma unroll
+            for (int nt = 0; nt < KS; ++nt) {
+                float d[4] = {bl2[nt][0], bl2[nt][1], bl2[nt][0], bl2[nt][1]};
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    if constexpr (sizeof(ST) == 4) mma_tf32(d, al[ks], b1h[ks][nt]);
+                    mma_tf32(d, ah[ks], b1l[ks][nt]);
+                    mma_tf32(d, ah[ks], b1h[ks][nt]);
+                }
+                if constexpr (MASKED) {
+                    const int col = t * 16 + 2 * gid;
+                    if (col >= N) d[0] = d[1] = -INFINITY;          // columns 2gid / 2gid+1 of the tile
+                    if (col + 1 >= N) d[2] = d[3] = -INFINITY;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sp[t][nt][e] = d[e];
+                mx[nt][0] = fmaxf(mx[nt][0], fmaxf(d[0], d[2]));
+                mx[nt][1] = fmaxf(mx[nt][1], fmaxf(d[1], d[3]));
+            }
+        };
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            if (t < nfull) logits_tile(Th2False(), t);
+            else logits_tile(Th2True(), t);
         }
         float sum[KS][2], inv[KS][2];
 #pragma unroll
@@ -221,33 +268,40 @@ th_mix2_fwd_kernel(const ST* __restrict__ S, const float* __restrict__ wl, const
                     rowsum[((long long)b * H + g) * N + i] = s;
                 }
             }
-        __nv_bfloat16* Prow = Pm + ((long long)b * H * N + i) * Np;
+        __nv_bfloat16* Prow = Pm + base;
+        auto probs_tile = [&](auto masked_c, int t) {
+            constexpr bool MASKED = decltype(masked_c)::value;
+            uint32_t a[KS][4];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            {
-                const int col = t * 16 + 2 * gid;
-                uint32_t a[KS][4];
+            for (int ks = 0; ks < KS; ++ks) {
+                float c[4];
 #pragma unroll
-                for (int ks = 0; ks < KS; ++ks) {
-                    float c[4];
+                for (int e = 0; e < 4; ++e) c[e] = sp[t][ks][e] * inv[ks][e & 1];
+                th2_c_to_a(c, a[ks]);
+            }
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) c[e] = sp[t][ks][e] * inv[ks][e & 1];
-                    th2_c_to_a(c, a[ks]);
-                }
+            for (int nt = 0; nt < KS; ++nt) {
+                float d[4] = {bw2[nt][0], bw2[nt][1], bw2[nt][0], bw2[nt][1]};
 #pragma unroll
-                for (int nt = 0; nt < KS; ++nt) {
-                    float d[4] = {bw2[nt][0], bw2[nt][1], bw2[nt][0], bw2[nt][1]};
-#pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) mma_tf32(d, a[ks], b2[ks][nt]);
+                for (int ks = 0; ks < KS; ++ks) mma_tf32(d, a[ks], b2[ks][nt]);
+                if constexpr (MASKED) {
+                    const int col = t * 16 + 2 * gid;
                     if (col < Np) {
-                        const int g0 = 8 * nt + 2 * tig;
                         const float v00 = col < N ? d[0] : 0.f, v01 = col + 1 < N ? d[2] : 0.f;   // head g0, cols col, col+1
                         const float v10 = col < N ? d[1] : 0.f, v11 = col + 1 < N ? d[3] : 0.f;   // head g0+1
-                        if (g0 < H) *reinterpret_cast<uint32_t*>(Prow + g0 * plane + col) = pack_bf16(v00, v01);
-                        if (g0 + 1 < H) *reinterpret_cast<uint32_t*>(Prow + (g0 + 1) * plane + col) = pack_bf16(v10, v11);
+                        if (off.c_ok[nt][0]) *reinterpret_cast<uint32_t*>(Prow + off.c[nt][0] + t * 16) = pack_bf16(v00, v01);
+                        if (off.c_ok[nt][1]) *reinterpret_cast<uint32_t*>(Prow + off.c[nt][1] + t * 16) = pack_bf16(v10, v11);
                     }
+                } else {
+                    if (off.c_ok[nt][0]) *reinterpret_cast<uint32_t*>(Prow + off.c[nt][0] + t * 16) = pack_bf16(d[0], d[2]);
+                    if (off.c_ok[nt][1]) *reinterpret_cast<uint32_t*>(Prow + off.c[nt][1] + t * 16) = pack_bf16(d[1], d[3]);
                 }
             }
+        };
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            if (t < nfull) probs_tile(Th2False(), t);
+            else probs_tile(Th2True(), t);
         }
     }
 }

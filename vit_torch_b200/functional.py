@@ -294,7 +294,7 @@ class BlockFn(torch.autograd.Function):
         if dqkvb is not None and not attn_dbias_done:
             ops.colsum_accum(dqkv, dqkvb)
         # ---- LN1 backward + residual; the bf16 copy is handed to the previous block through a side channel
-        side_sum = torch.zeros((D,), dtype=torch.float32, device=dev)
+        side_sum = grad_zeros((D,), dev)       # (arena slice: zeroed by the step's single memset)
         dx0, dx0b = ops.layernorm_bwd(dh1, x0, n1w, mean1, rstd1, dres=dx1, dweight=dn1w, dbias=dn1b, want_bf16=True,
                                       dxsum=side_sum)
         dx = dx0.view(B, N, D)
