@@ -390,7 +390,7 @@ def main():
     ap.add_argument("--e2e-sync-read", action="store_true",
                     help="e2e: read each step's loss with a blocking .item() right after enqueueing it (A/B; default: "
                          "the read of step i happens after step i+1 has been enqueued)")
-    ap.add_argument("--dp", default="auto", choices=["auto", "deferred", "overlap", "bf16", "split"],
+    ap.add_argument("--dp", default="auto", choices=["auto", "deferred", "overlap", "bf16", "split", "registered"],
                     help="DP gradient exchange: deferred = one fp32 all-reduce over the gradient arena after backward; "
                          "bf16 = the same in bf16; split = backward captured as two graphs, the first half's all-reduce "
                          "runs on --nccl-ctas thread blocks under the second graph; overlap = per-block all-reduces "
@@ -420,7 +420,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dp_mode = "none" if world == 1 else ("split" if args.dp == "auto" else args.dp)
+    # auto: split wins at 2 GPUs (19.20 vs 19.36 ms/step) and loses at 8 (20.67 vs 20.10: the 4-CTA side communicator
+    # cannot move 2/3 of the arena under one third of backward there), profiles/r02_summary.md section 4
+    dp_mode = "none" if world == 1 else (("split" if world == 2 else "deferred") if args.dp == "auto" else args.dp)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         from vit_torch_b200.dist import configure_sm_partition
@@ -437,7 +439,8 @@ def main():
     reducer = None
     if world > 1:
         reducer = GradAllReducer(model, overlap=(dp_mode == "overlap"), compress=(dp_mode == "bf16"),
-                                 split=(dp_mode == "split"), split_ctas=args.nccl_ctas)
+                                 split=(dp_mode == "split"), split_ctas=args.nccl_ctas,
+                                 register_arena=(dp_mode == "registered"))
     trainer = train.Trainer(model, lr=1e-3, momentum=0.9, reducer=reducer, graph=(not args.no_graph), strict_graph=True)
 
     x_host, y_host = synth_batch(bs, w["size"], 1000 + rank, args.input)
@@ -644,7 +647,12 @@ def main():
                                           "split": "backward replayed as two CUDA graphs; the fp32 gradients of the last "
                                                    "two thirds of the blocks are all-reduced on a side stream by a "
                                                    f"communicator capped at {args.nccl_ctas} thread blocks while the second "
-                                                   "graph runs; the remaining third is reduced after it"}[dp_mode]},
+                                                   "graph runs; the remaining third is reduced after it",
+                                          "registered": "one NCCL all-reduce over the fp32 gradient arena after backward; "
+                                                        "the arena lives in ncclMemAlloc memory registered with the "
+                                                        "communicator (zero-copy NVLS): "
+                                                        + ("registered" if getattr(reducer, "arena_registered", False)
+                                                           else "registration unavailable, plain buffer")}[dp_mode]},
             "step_tflops_per_gpu": step_fl / (ms / args.steps * 1e-3) / 1e12,
             "step_frac_of_bf16_peak": step_fl / (ms / args.steps * 1e-3) / 1e12 / pk["bf16_sustained"],
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,

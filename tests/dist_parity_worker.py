@@ -29,11 +29,14 @@ def main():
         return m
 
     m = make()
-    red = GradAllReducer(m, overlap=(mode == "overlap"), compress=(mode == "bf16"), split=(mode == "split"))
+    red = GradAllReducer(m, overlap=(mode == "overlap"), compress=(mode == "bf16"), split=(mode == "split"),
+                         register_arena=(mode == "registered"))
     tr = train.Trainer(m, lr=0.0, momentum=0.0, reducer=red, graph=(mode != "overlap"), strict_graph=True)
     x, y = X[rank * bs:(rank + 1) * bs].to(dev), Y[rank * bs:(rank + 1) * bs].to(dev)
     for _ in range(4):                       # 2 eager steps, the capture step, one replay (lr 0: weights unchanged)
         tr.step(x, y)
+    if mode == "registered" and rank == 0:
+        print(f"arena registered with NCCL: {red.arena_registered}", flush=True)
     if mode == "split":
         assert tr._graph2 is not None and 0 < tr._split_off < tr.arena.off, "backward was not split into two graphs"
     torch.cuda.synchronize()

@@ -49,8 +49,13 @@ def partition_limit(nccl_ctas: int) -> int:
 
 class GradAllReducer:
     def __init__(self, model: torch.nn.Module, process_group=None, overlap: bool = True, compress: bool = False,
-                 split: bool = False, split_ctas: int = 4):
+                 split: bool = False, split_ctas: int = 4, register_arena: bool = False):
         self.model = model
+        # register_arena: the Trainer's gradient arena is allocated by NCCL's own allocator (ncclMemAlloc) and registered
+        # with the communicator, so that NVLS (in-switch) all-reduces read and write it zero-copy
+        self.register_arena = bool(register_arena)
+        self.arena_registered = False
+        self._pools = []
         self.compress = bool(compress) and not overlap     # deferred mode only: bf16 gradients on the wire
         self._wire = None
         # split mode (graph Trainer): backward is captured as two graphs; the gradients of the first half (the last
@@ -76,6 +81,27 @@ class GradAllReducer:
         self._limited = False
         if self.world > 1:
             Fn.grad_bucket_hooks.append(self._on_bucket)
+
+    def alloc_arena(self, numel: int, device):
+        """Zeroed fp32 buffer from the communicator's registered memory pool, or None (plain allocation) when
+        registration was not asked for or this torch / NCCL build cannot do it."""
+        if not self.register_arena or not (dist.is_initialized() and self.world > 1 and self.cuda):
+            return None
+        try:
+            pg = self.pg if self.pg is not None else dist.group.WORLD
+            backend = pg._get_backend(torch.device(device))
+            pool = torch.cuda.MemPool(backend.mem_allocator)
+            with torch.cuda.use_mem_pool(pool):
+                buf = torch.zeros((int(numel),), dtype=torch.float32, device=device)
+            backend.register_mem_pool(pool)
+            self._pools.append(pool)          # the pool owns the memory: keep it alive as long as the reducer
+            self.arena_registered = True
+            return buf
+        except Exception as exc:              # older NCCL / torch without ncclMemAlloc: fall back to a plain buffer
+            import sys
+            print(f"[vit_torch_b200] gradient arena not registered with NCCL ({type(exc).__name__}: {exc})",
+                  file=sys.stderr)
+            return None
 
     def close(self):
         if self._on_bucket in Fn.grad_bucket_hooks:

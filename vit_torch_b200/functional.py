@@ -45,8 +45,11 @@ class GradArena:
     because the blocks' buffers are then adjacent, a data-parallel step can all-reduce them with ONE collective
     (dist.GradAllReducer, deferred mode). Gradients handed out are views: they are valid until the next begin()."""
 
-    def __init__(self, numel: int, device):
-        self.buf = torch.zeros((max(int(numel), 4),), dtype=torch.float32, device=device)
+    def __init__(self, numel: int, device, alloc=None):
+        # alloc(numel, device) -> zeroed fp32 tensor or None: lets a data-parallel reducer place the arena in memory
+        # registered with its communicator (dist.GradAllReducer.alloc_arena)
+        buf = alloc(max(int(numel), 4), device) if alloc is not None else None
+        self.buf = buf if buf is not None else torch.zeros((max(int(numel), 4),), dtype=torch.float32, device=device)
         self.off = 0
         self.high = 0            # high-water mark of the last step: only that part needs zeroing / reducing
 

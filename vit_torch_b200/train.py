@@ -277,7 +277,7 @@ class Trainer:
             # (+ slack: the head's weight gradients are padded to 8 rows, d_pos doubles as the source of d_cls / d_bias)
             self.arena = functional.GradArena(sum((p.numel() + 3) // 4 * 4 + 4 for p in params) + (1 << 16)
                                               + 2 * max((p.numel() for p in params if p.dim() == 3), default=0),
-                                              params[0].device)
+                                              params[0].device, alloc=getattr(reducer, "alloc_arena", None))
         # Data parallel: with the deferred all-reduce (dist.GradAllReducer(overlap=False)) forward + loss + backward are
         # captured and the collective and the optimiser kernel run eagerly after the replay; the overlapped mode issues
         # NCCL calls from inside backward and stays eager.
