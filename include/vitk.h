@@ -292,13 +292,15 @@ int vitk_th_mix_bwd_s16(const void* S_bf16, const void* dPm_bf16, const float* r
  *                    pad columns [N, Np) are written as zeros)
  *   vitk_th_apply  : out[b*N+i, o_col0+h*d+e] = sum_j p[b,h,i,j] * x[b*N+j, x_col0+h*d+e]    (transpose = 0)
  *                    out[b*N+j, o_col0+h*d+e] = sum_i p[b,h,i,j] * x[b*N+i, x_col0+h*d+e]    (transpose = 1)
- *                    p bf16 planes whose pad columns are zero (as vitk_th_mix_* write them); out bf16 [B*N, ldo].
+ *                    p bf16 planes whose pad columns are zero (as vitk_th_mix_* write them); out bf16 [B*N, ldo];
+ *                    colsum: optional fp32 [H*d], += column sums of the H*d output columns (the slice of the qkv bias
+ *                    gradient that belongs to this product: autograd of `self.qkv` with qkv_bias, models/cait.py:99).
  */
 int vitk_th_gemm_supported(int N, int d, int Np);
 int vitk_th_scores(const void* a_bf16, long long lda, int a_cols, int a_col0, const void* b_bf16, long long ldb, int b_cols,
                    int b_col0, void* out, int out_f32, int B, int N, int H, int d, int Np, void* stream);
 int vitk_th_apply(const void* p_bf16, const void* x_bf16, long long ldx, int x_cols, int x_col0, void* out_bf16,
-                  long long ldo, int o_col0, int transpose, int B, int N, int H, int d, int Np, void* stream);
+                  long long ldo, int o_col0, int transpose, float* colsum, int B, int N, int H, int d, int Np, void* stream);
 
 /*
  * CaiT class attention (models/cait.py:38-55): one query row per (image, head). q bf16 [B,C] (unscaled), keys/values:

@@ -1,9 +1,12 @@
-"""LayerNorm fwd/bwd achieved HBM bandwidth at the ViT-B/16 bs128 shape (env VITK_LN_RING=0: register kernel)."""
+"""LayerNorm fwd/bwd achieved HBM bandwidth at the ViT-B/16 bs128 shape, or `python scripts/bench_ln.py M D`
+(env VITK_LN_RING=0: register kernel; VITK_LN_RING_ROWS=r: rows per ring stage)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from vit_torch_b200 import ops
 M, D, NB = 25216, 768, 4
+if len(sys.argv) > 2:
+    M, D = int(sys.argv[1]), int(sys.argv[2])
 xs = [torch.randn(M, D, device="cuda") for _ in range(NB)]
 dys = [torch.randn(M, D, device="cuda").bfloat16() for _ in range(NB)]
 drs = [torch.randn(M, D, device="cuda") for _ in range(NB)]
@@ -25,4 +28,4 @@ def bwd():
     j = i[0] % NB; i[0] += 1
     ops.layernorm_bwd(dys[j], xs[j], w, mean, rstd, dres=drs[j], dweight=dw, dbias=db, want_bf16=True, dxsum=ds)
 tf, tb = timeit(fwd), timeit(bwd)
-print(f"ring={os.environ.get('VITK_LN_RING', '1')} ln_fwd {tf*1e6:.1f} us {M*D*6/tf/1e12:.2f} TB/s | ln_bwd {tb*1e6:.1f} us {M*D*16/tb/1e12:.2f} TB/s")
+print(f"M={M} D={D} ring={os.environ.get('VITK_LN_RING', '1')} rows/stage={os.environ.get('VITK_LN_RING_ROWS', 'auto')} ln_fwd {tf*1e6:.1f} us {M*D*6/tf/1e12:.2f} TB/s | ln_bwd {tb*1e6:.1f} us {M*D*16/tb/1e12:.2f} TB/s")

@@ -59,9 +59,10 @@ def test_th_apply_matches_einsum(B, N, H, d):
     # transposed products into column slices of one [B*N, 3D] buffer: dV = P^T dO (slice 2), dK = P^T q (slice 1)
     do = torch.randn(B * N, D, device="cuda").bfloat16()
     dqkv = torch.zeros(B * N, 3 * D, device="cuda").bfloat16()
-    ops.th_apply(P, do, 0, dqkv, 2 * D, B, N, H, d, Np, transpose=True)
-    ops.th_apply(P, qkv, 0, dqkv, D, B, N, H, d, Np, transpose=True)
-    ops.th_apply(P, qkv, D, dqkv, 0, B, N, H, d, Np)
+    dbias = torch.full((3 * D,), 0.5, device="cuda")        # column sums are ACCUMULATED into the slices
+    ops.th_apply(P, do, 0, dqkv, 2 * D, B, N, H, d, Np, transpose=True, colsum=dbias[2 * D:])
+    ops.th_apply_t(P, qkv, 0, dqkv, D, B, N, H, d, Np, colsum=dbias[D:2 * D])
+    ops.th_apply(P, qkv, D, dqkv, 0, B, N, H, d, Np, colsum=dbias[:D])
     q = qkv[:, :D].float().view(B, N, H, d)
     k = qkv[:, D:2 * D].float().view(B, N, H, d)
     ref_dv = torch.einsum("bhij,bihe->bjhe", Pf, do.float().view(B, N, H, d)).reshape(B * N, D)
@@ -70,6 +71,8 @@ def test_th_apply_matches_einsum(B, N, H, d):
     assert nerr(dqkv[:, 2 * D:], ref_dv) <= 5e-3
     assert nerr(dqkv[:, D:2 * D], ref_dk) <= 5e-3
     assert nerr(dqkv[:, :D], ref_dq) <= 5e-3
+    ref_bias = torch.cat([ref_dq.sum(0), ref_dk.sum(0), ref_dv.sum(0)]) + 0.5
+    assert nerr(dbias, ref_bias) <= 1e-3
 
 
 def test_th_gemm_rejects_long_sequences():

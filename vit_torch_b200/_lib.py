@@ -58,7 +58,7 @@ SIGNATURES = {
     "vitk_th_mix_bwd_s16": [_P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "vitk_th_gemm_supported": [_I, _I, _I],
     "vitk_th_scores": [_P, _L, _I, _I, _P, _L, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
-    "vitk_th_apply": [_P, _P, _L, _I, _I, _P, _L, _I, _I, _I, _I, _I, _I, _I, _P],
+    "vitk_th_apply": [_P, _P, _L, _I, _I, _P, _L, _I, _I, _P, _I, _I, _I, _I, _I, _P],
     "vitk_class_attn_fwd": [_P, _P, _P, _P, _P, _L, _L, _F, _P, _P, _I, _I, _I, _I, _P],
     "vitk_class_attn_bwd": [_P, _P, _P, _P, _P, _L, _L, _P, _P, _F, _P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _I, _P],
     "vitk_attn_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],

@@ -192,6 +192,9 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long lo
 // counted on an mbarrier per stage), so LNR_STAGES rows per SM are always in flight; eight consumer warps take the
 // rows round-robin, keep xhat / dy*w of the row and the dweight / dbias / column-sum partials in registers, and store
 // dx (fp32) and its bf16 copy straight from registers.
+// A stage holds R consecutive rows (R > 1 when the rows are contiguous in memory): the single producer thread issues
+// three bulk copies per STAGE, and at D = 384 one row per stage left the kernel bound by that thread's issue rate
+// (50 us for 154 MB, 510 copies per SM); a block owns a contiguous range of rows for this.
 // ------------------------------------------------------------------------------------------------
 constexpr int LNR_CONSUMERS = 8;
 constexpr int LNR_THREADS = (LNR_CONSUMERS + 1) * 32;
@@ -209,12 +212,12 @@ ln_bwd_ring_kernel(const void* __restrict__ dy_, const float* __restrict__ x, lo
                    const float* __restrict__ w, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                    const float* __restrict__ dres, float* __restrict__ dx, long long dx_stride,
                    __nv_bfloat16* __restrict__ dx_bf16, const float* __restrict__ colscale, float* __restrict__ dweight,
-                   float* __restrict__ dbias, float* __restrict__ dxsum, long long rows, int D, int stages) {
+                   float* __restrict__ dbias, float* __restrict__ dxsum, long long rows, int D, int stages, int R) {
     constexpr int Dp = MAXC * 128;
     extern __shared__ __align__(128) uint8_t lnr_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t x_bytes = D * 4, r_bytes = (dres != nullptr) ? D * 4 : 0, dy_bytes = D * (DY_F32 ? 4 : 2);
-    const uint32_t stage_bytes = ((x_bytes + D * 4 + D * (DY_F32 ? 4 : 2)) + 127) & ~127u;
+    const uint32_t stage_bytes = ((uint32_t)R * (x_bytes + D * 4 + D * (DY_F32 ? 4 : 2)) + 127) & ~127u;
     uint8_t* ring = lnr_smem;
     float* sw = reinterpret_cast<float*>(lnr_smem + (size_t)stages * stage_bytes);
     uint64_t* full = reinterpret_cast<uint64_t*>(sw + Dp);
@@ -223,13 +226,16 @@ ln_bwd_ring_kernel(const void* __restrict__ dy_, const float* __restrict__ x, lo
     if (threadIdx.x == 0) {
         for (int i = 0; i < stages; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
+            mbar_init(&empty[i], R);      // one arrival per row of the stage
         }
         fence_mbar_init();
     }
     __syncthreads();
-    // rows of this block: blockIdx.x, blockIdx.x + gridDim.x, ...
-    const long long nloc = (rows - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    // rows of this block: the contiguous range [row0, row0 + nloc)
+    const long long per_block = (rows + gridDim.x - 1) / gridDim.x;
+    const long long row0 = (long long)blockIdx.x * per_block;
+    const long long nloc = row0 >= rows ? 0 : (rows - row0 < per_block ? rows - row0 : per_block);
+    const long long ngroups = (nloc + R - 1) / R;
     float4 aw[MAXC], ab[MAXC], ax[MAXC];
 #pragma unroll
     for (int i = 0; i < MAXC; ++i) aw[i] = ab[i] = ax[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -239,15 +245,18 @@ ln_bwd_ring_kernel(const void* __restrict__ dy_, const float* __restrict__ x, lo
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (long long k = 0; k < nloc; ++k) {
-                const long long row = blockIdx.x + k * gridDim.x;
+            for (long long g = 0; g < ngroups; ++g) {
+                const long long row = row0 + g * R;
+                const uint32_t nr = (uint32_t)(nloc - g * R < R ? nloc - g * R : R);    // rows of this stage
+                // (a short last group never completes its `empty` phase: nothing waits on it any more)
                 mbar_wait(&empty[s], ph ^ 1);
                 uint8_t* st = ring + (size_t)s * stage_bytes;
-                mbar_expect_tx(&full[s], x_bytes + r_bytes + dy_bytes);
-                bulk_g2s(st, x + row * x_stride, x_bytes, &full[s]);
-                if (r_bytes) bulk_g2s(st + x_bytes, dres + row * dx_stride, r_bytes, &full[s]);
-                bulk_g2s(st + 2 * x_bytes, reinterpret_cast<const uint8_t*>(dy_) + (size_t)row * dy_bytes, dy_bytes,
-                         &full[s]);
+                mbar_expect_tx(&full[s], nr * (x_bytes + r_bytes + dy_bytes));
+                // (R > 1 only with x_stride == dx_stride == D: the rows of a stage are one contiguous range)
+                bulk_g2s(st, x + row * x_stride, nr * x_bytes, &full[s]);
+                if (r_bytes) bulk_g2s(st + (size_t)R * x_bytes, dres + row * dx_stride, nr * r_bytes, &full[s]);
+                bulk_g2s(st + (size_t)2 * R * x_bytes, reinterpret_cast<const uint8_t*>(dy_) + (size_t)row * dy_bytes,
+                         nr * dy_bytes, &full[s]);
                 if (++s == stages) { s = 0; ph ^= 1; }
             }
         }
@@ -255,14 +264,17 @@ ln_bwd_ring_kernel(const void* __restrict__ dy_, const float* __restrict__ x, lo
         // ===================== consumers =====================
         const float inv_d = 1.0f / static_cast<float>(D);
         for (long long k = warp; k < nloc; k += LNR_CONSUMERS) {
-            const long long row = blockIdx.x + k * gridDim.x;
-            const int s = static_cast<int>(k % stages);
-            const uint32_t ph = static_cast<uint32_t>((k / stages) & 1);
+            const long long row = row0 + k;
+            const long long g = k / R;
+            const int rr = static_cast<int>(k - g * R);          // row inside its stage
+            const int s = static_cast<int>(g % stages);
+            const uint32_t ph = static_cast<uint32_t>((g / stages) & 1);
             const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
             mbar_wait(&full[s], ph);
             const uint8_t* st = ring + (size_t)s * stage_bytes;
-            const float* sx = reinterpret_cast<const float*>(st);
-            const float* sr = reinterpret_cast<const float*>(st + x_bytes);
+            const float* sx = reinterpret_cast<const float*>(st + (size_t)rr * x_bytes);
+            const float* sr = reinterpret_cast<const float*>(st + (size_t)(R + rr) * x_bytes);
+            const uint8_t* sdy = st + (size_t)2 * R * x_bytes + (size_t)rr * dy_bytes;
             float4 xh[MAXC], gv[MAXC];
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -272,10 +284,9 @@ ln_bwd_ring_kernel(const void* __restrict__ dy_, const float* __restrict__ x, lo
                     const float4 xv = *reinterpret_cast<const float4*>(sx + c);
                     float4 dv;
                     if constexpr (DY_F32) {
-                        dv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(st + 2 * x_bytes) + c);
+                        dv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sdy) + c);
                     } else {
-                        const uint2 t = *reinterpret_cast<const uint2*>(
-                            reinterpret_cast<const __nv_bfloat16*>(st + 2 * x_bytes) + c);
+                        const uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(sdy) + c);
                         dv = make_float4(bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y));
                     }
                     const float4 wv = *reinterpret_cast<const float4*>(sw + c);
@@ -850,7 +861,19 @@ static int ln_bwd_impl(const void* dy, int dy_is_f32, const float* x, long long 
         ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dres)) & 15) == 0) {
         const int cpad = chunks <= 2 ? 2 : chunks <= 3 ? 3 : chunks <= 6 ? 6 : 8;
         const int Dp = cpad * 128;
-        const unsigned stage_bytes = ((unsigned)(D * 4 + D * 4 + D * (dy_is_f32 ? 4 : 2)) + 127u) & ~127u;
+        // rows per stage: ~8 KB stages when the rows are contiguous (three bulk copies per stage, not per row)
+        const unsigned row_bytes = (unsigned)(D * 4 + D * 4 + D * (dy_is_f32 ? 4 : 2));
+        int R = 1;
+        {
+            static int r_forced = -1;
+            if (r_forced < 0) { const char* e = getenv("VITK_LN_RING_ROWS"); r_forced = e ? atoi(e) : 0; }
+            if (x_stride == D && (dres == nullptr || dx_stride == D)) {
+                R = r_forced > 0 ? r_forced : (int)(8192 / row_bytes);
+                if (R < 1) R = 1;
+                if (R > 8) R = 8;
+            }
+        }
+        const unsigned stage_bytes = ((unsigned)R * row_bytes + 127u) & ~127u;
         const long long fixed = (long long)Dp * 4 + 2 * 64 * 8 + 256;
         int stages = (int)((220 * 1024 - fixed) / stage_bytes);
         if (stages > 32) stages = 32;
@@ -870,7 +893,7 @@ static int ln_bwd_impl(const void* dy, int dy_is_f32, const float* x, long long 
         }                                                                                                             \
         ln_bwd_ring_kernel<C, F><<<grid, LNR_THREADS, smem, st>>>(dy, x, x_stride, weight, mean, rstd, dres, dx,      \
                                                                   dx_stride, dxb, colscale, dweight, dbias, dxsum,   \
-                                                                  rows, D, stages);                                   \
+                                                                  rows, D, stages, R);                                \
     } while (0)
 #define VITK_LN_RING(C)                           \
     do {                                          \

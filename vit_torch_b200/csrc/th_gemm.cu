@@ -38,6 +38,7 @@ struct ThGemmArgs {
     long long ldo;
     int o_col0;
     int out_f32;
+    float* colsum;          // th_apply*: optional fp32 [H*d], += column sums of the output (bias gradient of the qkv Linear)
 };
 
 __device__ __forceinline__ uint4 pack8_bf16(const uint32_t* v) {
@@ -337,9 +338,17 @@ th_apply_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
             mbar_wait(&acc_full[as], (ai >> 1) & 1);
             tc_fence_after_sync();
             auto store16 = [&](int ch, const uint32_t* v) {      // 16 columns of this lane's row -> 32 bytes of bf16
-                if (!row_ok) return;
-                st_v4(orow + ch * 16, pack8_bf16(v));
-                st_v4(orow + ch * 16 + 8, pack8_bf16(v + 8));
+                if (row_ok) {
+                    st_v4(orow + ch * 16, pack8_bf16(v));
+                    st_v4(orow + ch * 16 + 8, pack8_bf16(v + 8));
+                }
+                if (a.colsum != nullptr) {                       // (warp-uniform) 16-shuffle reduction over the 32 rows
+                    float f[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = row_ok ? __uint_as_float(v[i]) : 0.f;
+                    const float tot = warp_colsum16(f, lane);
+                    if ((lane & 1) == 0) atomicAdd(a.colsum + h0 * HD + ch * 16 + warp_colsum16_col(lane), tot);
+                }
             };
             int ch = ch0;
             for (; ch + 2 <= ch1; ch += 2) {
@@ -467,13 +476,15 @@ extern "C" int vitk_th_scores(const void* a_bf16, long long lda, int a_cols, int
     a.HG = 1;
     a.a_col0 = a_col0; a.b_col0 = b_col0;
     a.out = out; a.ldo = Np; a.o_col0 = 0; a.out_f32 = out_f32 ? 1 : 0;
+    a.colsum = nullptr;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (d == 64) return launch_th_scores<64>(a_bf16, lda, a_cols, b_bf16, ldb, b_cols, a, st);
     return launch_th_scores<48>(a_bf16, lda, a_cols, b_bf16, ldb, b_cols, a, st);
 }
 
 extern "C" int vitk_th_apply(const void* p_bf16, const void* x_bf16, long long ldx, int x_cols, int x_col0, void* out_bf16,
-                             long long ldo, int o_col0, int transpose, int B, int N, int H, int d, int Np, void* stream) {
+                             long long ldo, int o_col0, int transpose, float* colsum, int B, int N, int H, int d, int Np,
+                             void* stream) {
     if (!p_bf16 || !x_bf16 || !out_bf16 || !th_gemm_shape_ok(B, N, H, d, Np)) return VITK_ERR_ARG;
     if ((ldx % 8) != 0 || (ldo % 8) != 0 || (o_col0 % 8) != 0 || x_col0 < 0 || x_col0 + H * d > x_cols || x_cols > ldx ||
         o_col0 < 0 || o_col0 + H * d > ldo)
@@ -485,6 +496,7 @@ extern "C" int vitk_th_apply(const void* p_bf16, const void* x_bf16, long long l
     a.HG = th_apply_heads_per_item(B, N, H, d);
     a.a_col0 = 0; a.b_col0 = x_col0;
     a.out = out_bf16; a.ldo = ldo; a.o_col0 = o_col0; a.out_f32 = 0;
+    a.colsum = colsum;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (d == 64) {
         if (transpose) return launch_th_apply<64, true>(p_bf16, x_bf16, ldx, x_cols, a, st);

@@ -263,14 +263,17 @@ class BlockFn(torch.autograd.Function):
             dthw_b = dthw_b if dthw_b is not None else zeros(thw_b)
             dqkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
             if ops.th_gemm_ok(N, d, Np) and (S.dtype == torch.bfloat16 or ops.th_mix_bf16_dp(Np)):
+                # (the three products also reduce their outputs over rows: the qkv bias gradient, no separate pass)
+                cs = (lambda k: dqkvb[k * D:(k + 1) * D]) if dqkvb is not None else (lambda k: None)
                 dPm = ops.th_scores(do, 0, qkv, 2 * D, B, N, H, d, Np)                  # dP'[i,j] = dO_i . v_j (bf16)
-                ops.th_apply_t(Pm, do, 0, dqkv, 2 * D, B, N, H, d, Np)                  # dV = P'^T dO
+                ops.th_apply_t(Pm, do, 0, dqkv, 2 * D, B, N, H, d, Np, colsum=cs(2))    # dV = P'^T dO
                 dS = ops.th_mix_bwd(S, dPm, rmax, rsum, thl_w, thl_b, thw_w, thw_b, scale, dthl_w, dthl_b, dthw_w,
                                     dthw_b, B, H, N, Np)
                 del dPm
-                ops.th_apply(dS, qkv, D, dqkv, 0, B, N, H, d, Np)                       # dQ = dS K
-                ops.th_apply_t(dS, qkv, 0, dqkv, D, B, N, H, d, Np)                     # dK = dS^T Q
+                ops.th_apply(dS, qkv, D, dqkv, 0, B, N, H, d, Np, colsum=cs(0))         # dQ = dS K
+                ops.th_apply_t(dS, qkv, 0, dqkv, D, B, N, H, d, Np, colsum=cs(1))       # dK = dS^T Q
                 del dS
+                attn_dbias_done = dqkvb is not None
             else:
                 dp16 = ops.th_mix_bf16_dp(Np)       # version-2 mixing kernels read dP' in bf16
                 dPm = torch.empty((B, H, N, Np), dtype=torch.bfloat16 if dp16 else torch.float32, device=dev)

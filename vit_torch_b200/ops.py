@@ -409,21 +409,25 @@ def th_scores(a, a_col0, b, b_col0, B, N, H, d, Np, out_f32=False):
     return out
 
 
-def th_apply(p, x, x_col0, out, o_col0, B, N, H, d, Np, transpose=False):
+def th_apply(p, x, x_col0, out, o_col0, B, N, H, d, Np, transpose=False, colsum=None):
     """out[b*N+i, o_col0+h*d+e] = sum_j p[b,h,i,j] x[b*N+j, x_col0+h*d+e]  (transpose: sum over i of p[b,h,i,j] x[b*N+i, ..]
-    into row j). p: bf16 plane [B,H,N,Np] with zero pad columns; x, out: token-major bf16."""
+    into row j). p: bf16 plane [B,H,N,Np] with zero pad columns; x, out: token-major bf16. colsum (fp32 [H*d]) += the
+    column sums of the written output."""
     global launch_count
     _need_cuda(p, x, out)
     assert p.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+    if colsum is not None:
+        _need_cuda(colsum)
+        assert colsum.dtype == torch.float32 and colsum.is_contiguous() and colsum.numel() == H * d
     check(_lib.load().vitk_th_apply(ptr(p), ptr(x), x.stride(0), x.shape[1], x_col0, ptr(out), out.stride(0), o_col0,
-                                    int(transpose), B, N, H, d, Np, _stream()), "vitk_th_apply")
+                                    int(transpose), ptr(colsum), B, N, H, d, Np, _stream()), "vitk_th_apply")
     launch_count += 1
     return out
 
 
-def th_apply_t(p, x, x_col0, out, o_col0, B, N, H, d, Np):
+def th_apply_t(p, x, x_col0, out, o_col0, B, N, H, d, Np, colsum=None):
     """th_apply with the plane transposed: out[b*N+j] = sum_i p[b,h,i,j] x[b*N+i]."""
-    return _th_apply_impl(p, x, x_col0, out, o_col0, B, N, H, d, Np, transpose=True)
+    return _th_apply_impl(p, x, x_col0, out, o_col0, B, N, H, d, Np, transpose=True, colsum=colsum)
 
 
 def th_mix_fwd(S, wl, bl, ww, bw, scale, B, H, N, Np):
