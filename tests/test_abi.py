@@ -47,3 +47,16 @@ def test_bad_arguments_return_error_codes():
     assert lib.vitk_colsum_bf16(None, 8, 4, 8, None, None) == -1
     assert lib.vitk_attn_fwd(None, None, None, 1, 197, 6, 32, 0.125, None) == -1
     assert lib.vitk_patchify(None, None, 1, 3, 224, 224, 16, None) == -1
+
+
+def test_talking_heads_products_reject_bad_shapes():
+    """vitk_th_scores / vitk_th_apply validate before any launch: long sequences, odd head sizes, unaligned pitches."""
+    from vit_torch_b200 import _lib
+    lib = _lib.load()
+    assert lib.vitk_th_gemm_supported(196, 48, 200) == 1 and lib.vitk_th_gemm_supported(197, 64, 200) == 1
+    assert lib.vitk_th_gemm_supported(577, 48, 584) == 0        # CaiT at 384 px: generic batched GEMM instead
+    assert lib.vitk_th_gemm_supported(196, 32, 200) == 0        # head size
+    assert lib.vitk_th_gemm_supported(196, 48, 196) == 0        # plane pitch must be a multiple of 8
+    assert lib.vitk_th_scores(None, 1152, 1152, 0, None, 1152, 1152, 384, None, 0, 1, 196, 8, 48, 200, None) == -1
+    assert lib.vitk_th_apply(None, None, 1152, 1152, 768, None, 384, 0, 0, None, 1, 196, 8, 48, 200, None) == -1
+    assert lib.vitk_th_mix_fwd_s16(None, None, None, None, None, 0.1, None, None, None, 1, 8, 196, 200, None) == -1
