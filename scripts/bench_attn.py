@@ -29,6 +29,10 @@ for name, B, N, H, d in (("vitb16_bs128", 128, 197, 12, 64), ("vitb8_bs64", 64, 
     r = {"shape": name, "B": B, "N": N, "H": H, "d": d}
     r["fwd_us"] = timeit(lambda: ops.attn_fwd(qkv, B, N, H, d, scale))
     r["fwd_tflops"] = fl / r["fwd_us"] / 1e6
+    if os.environ.get("BENCH_ATTN_FWD_ONLY") == "1":
+        print(r, flush=True)
+        rows.append(r)
+        continue
     for variant, env in (("head", "1"), ("two_kernel", "0")):
         os.environ["VITK_ATTN_BWD_HEAD"] = env
         if variant == "head" and N > 256:
@@ -36,6 +40,9 @@ for name, B, N, H, d in (("vitb16_bs128", 128, 197, 12, 64), ("vitb8_bs64", 64, 
         r[f"bwd_{variant}_us"] = timeit(lambda: ops.attn_bwd(qkv, out, dout, lse2, B, N, H, d, scale, dbias=dbias))
         r[f"bwd_{variant}_tflops"] = 2.5 * fl / r[f"bwd_{variant}_us"] / 1e6
     os.environ.pop("VITK_ATTN_BWD_HEAD", None)     # default: two-kernel
+    if d == 64:     # single-kernel backward (S / dP computed once, dQ through fp32 atomics + conversion pass)
+        r["bwd_fused_us"] = timeit(lambda: ops.attn_bwd(qkv, out, dout, lse2, B, N, H, d, scale, fused=True, dbias=dbias))
+        r["bwd_fused_tflops"] = 2.5 * fl / r["bwd_fused_us"] / 1e6
     print(r, flush=True)
     rows.append(r)
 path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/bench_attn.json"

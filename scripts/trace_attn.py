@@ -51,6 +51,15 @@ stat("-> first S issued (1->2)", 1, 2)
 stat("start -> first scores visible (0->24)", 0, 24)
 for j in range(nt):
     stat(f"tile {j}: elementwise (24+2j -> 25+2j)", 24 + 2 * j, 25 + 2 * j)
+    if which == "fwd" and j < 4:      # finer split of the forward's elementwise pass (warp 0) and the other group's span
+        stat(f"tile {j}:   scores visible -> loaded, S released", 24 + 2 * j, 40 + 4 * j)
+        stat(f"tile {j}:   -> max / rescale / P buffer free", 40 + 4 * j, 41 + 4 * j)
+        stat(f"tile {j}:   -> exp, sums, pack, st.shared", 41 + 4 * j, 42 + 4 * j)
+        stat(f"tile {j}:   -> fence.proxy.async", 42 + 4 * j, 43 + 4 * j)
+        stat(f"tile {j}:   group 1 (warp 4) whole tile", 16 + 2 * j, 17 + 2 * j)
+        stat(f"tile {j}:   group 1 start - group 0 start", 24 + 2 * j, 16 + 2 * j)
+        stat(f"tile {j}:   warp 0 done -> MMA warp sees P of group 0", 25 + 2 * j, 56 + j)
+        stat(f"tile {j}:   warp 0 done -> MMA warp sees P of group 1", 25 + 2 * j, 3 + j)
     if j + 1 < nt: stat(f"tile {j}: done -> next scores visible", 25 + 2 * j, 26 + 2 * j)
     stat(f"tile {j}: elementwise done -> acc MMA issued", 25 + 2 * j, 8 + j)
 stat("last tile done -> accumulator visible (->60)", 25 + 2 * (nt - 1), 60)

@@ -48,6 +48,7 @@ struct AttnFwdArgs {
     float* lse2;         // [B, H, N]
     long long* trace;    // instrumented build only (VITK_TRACE), else nullptr
     int pf_dist;         // two-group kernel: CTA i pulls the tiles of CTA i + pf_dist into L2 (0 = off)
+    int mma_spin;        // two-group kernel: the MMA warp polls its barriers without back-off (VITK_ATTN_MMA_SPIN=1)
 };
 
 #ifdef VITK_TRACE
@@ -390,12 +391,18 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t q_addr = smem_u32(smem + AF2_SMEM_Q), p_addr = smem_u32(smem + AF2_SMEM_P);
+            // VITK_ATTN_MMA_SPIN=1: poll without back-off (A/B runs and traces)
+            const bool spin = a.mma_spin != 0;
+            auto wait = [&](uint64_t* bar, uint32_t parity) {
+                if (spin) mbar_wait(bar, parity);
+                else mbar_wait_backoff(bar, parity);
+            };
             auto issue_s = [&](int j) {
                 const int s = j % NS;
                 const int valid = min(AF_BKV, a.N - j * AF_BKV);
                 const int ncols = (valid + 15) & ~15;
-                mbar_wait_backoff(&k_full[s], (j / NS) & 1);
-                if (j > 0) mbar_wait_backoff(s_free, (j - 1) & 1);
+                wait(&k_full[s], (j / NS) & 1);
+                if (j > 0) wait(s_free, (j - 1) & 1);
                 tc_fence_after_sync();
                 const uint32_t idesc = make_idesc_bf16(128, ncols, 0, 0);
                 const uint64_t adesc = make_smem_desc_sw128(q_addr, 0, 1024);
@@ -405,7 +412,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 umma_commit(s_full);
             };
             VITK_TRACE_EV(a.trace, 1);
-            mbar_wait_backoff(q_full, 0);
+            wait(q_full, 0);
             issue_s(0);
             VITK_TRACE_EV(a.trace, 2);
             for (int j = 0; j < nkv; ++j) {
@@ -413,13 +420,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 if (j + 1 < nkv) issue_s(j + 1);
                 const int valid = min(AF_BKV, a.N - j * AF_BKV);
                 const int ksteps = (valid + 15) >> 4;
-                mbar_wait_backoff(&v_full[ks], (j / NS) & 1);
+                wait(&v_full[ks], (j / NS) & 1);
                 // O_g[128, HD] += P_j[128, 32g..32g+31] * V_j[32g..32g+31, HD]: A = P (K-major), B = V read MN-major
                 constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, 0, 1);
                 const uint32_t v_addr = smem_u32(smem + AF2_SMEM_V + ks * AF_KVTILE);
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
-                    mbar_wait_backoff(&p_full[2 * g + s], (j >> 1) & 1);
+                    wait(&p_full[2 * g + s], (j >> 1) & 1);
+                    if (j < 4) VITK_TRACE_EV(a.trace, (g == 0 ? 56 : 3) + j);
                     tc_fence_after_sync();
                     for (int k = 2 * g; k < ksteps && k < 2 * g + 2; ++k) {
                         const uint64_t adesc = make_smem_desc_sw128(p_addr + s * AF_QTILE + k * 32, 0, 1024);
@@ -449,6 +457,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             mbar_wait(s_full, j & 1);
             tc_fence_after_sync();
             if (threadIdx.x == 0 && j < 8) VITK_TRACE_EV(a.trace, 24 + 2 * j);
+            if (threadIdx.x == 128 && j < 4) VITK_TRACE_EV(a.trace, 16 + 2 * j);
             uint32_t sr[32];
             if (work) {
                 tmem_ld_32x32b_x32(tmem_s + lane_off + 32 * g, sr);
@@ -456,6 +465,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
             tc_fence_before_sync();
             mbar_arrive(s_free);
+            if (threadIdx.x == 0 && j < 4) VITK_TRACE_EV(a.trace, 40 + 4 * j);
             if (work) {
                 float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                 if (nv == 32) {
@@ -492,6 +502,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 }
                 // P buffer (j & 1) was last read by PV_{j-2}
                 if (j >= 2) mbar_wait(&o_full[j & 1], ((j - 2) >> 1) & 1);
+                if (threadIdx.x == 0 && j < 4) VITK_TRACE_EV(a.trace, 41 + 4 * j);
                 uint8_t* p_row = smem + AF2_SMEM_P + (j & 1) * AF_QTILE + row * 128;
                 float ps4[4] = {0.f, 0.f, 0.f, 0.f};
                 const float nm = -m_ref;
@@ -525,10 +536,13 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     }
                 }
                 l_run += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+                if (threadIdx.x == 0 && j < 4) VITK_TRACE_EV(a.trace, 42 + 4 * j);
                 fence_proxy_async_smem();
+                if (threadIdx.x == 0 && j < 4) VITK_TRACE_EV(a.trace, 43 + 4 * j);
             }
             mbar_arrive(&p_full[2 * g + (j & 1)]);
             if (threadIdx.x == 0 && j < 8) VITK_TRACE_EV(a.trace, 25 + 2 * j);
+            if (threadIdx.x == 128 && j < 4) VITK_TRACE_EV(a.trace, 17 + 2 * j);
         }
         // merge the two groups' partial softmax states, then each group writes half of the head's columns
         // (the Q tile is dead: its last reader, S of the last tile, completed before this group's last s_full wait)
@@ -667,6 +681,11 @@ extern "C" int vitk_attn_fwd(const void* qkv_bf16, void* out_bf16, float* lse2, 
     a.lse2 = lse2;
     a.trace = nullptr;
     a.pf_dist = attn_prefetch_dist();
+    {
+        static int spin = -1;
+        if (spin < 0) { const char* e = getenv("VITK_ATTN_MMA_SPIN"); spin = (e && e[0] == '1') ? 1 : 0; }
+        a.mma_spin = spin;
+    }
 #ifdef VITK_TRACE
     a.trace = g_attn_trace;
 #endif
