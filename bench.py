@@ -420,9 +420,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    # auto: split wins at 2 GPUs (19.20 vs 19.36 ms/step) and loses at 8 (20.67 vs 20.10: the 4-CTA side communicator
-    # cannot move 2/3 of the arena under one third of backward there), profiles/r02_summary.md section 4
-    dp_mode = "none" if world == 1 else (("split" if world == 2 else "deferred") if args.dp == "auto" else args.dp)
+    from vit_torch_b200.dist import default_mode
+    dp_mode = default_mode(world) if (args.dp == "auto" or world == 1) else args.dp
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         from vit_torch_b200.dist import configure_sm_partition

@@ -31,3 +31,29 @@ def test_flat_grads_carves_adjacent_zeroed_slices_from_the_arena():
     # without an arena every block allocates its own buffer
     buf3, _ = Fn._flat_grads([a], [True], dev)
     assert buf3.untyped_storage().data_ptr() != arena.buf.untyped_storage().data_ptr()
+
+
+def test_arena_takes_its_buffer_from_an_allocator_hook():
+    """A data-parallel reducer may place the arena in memory registered with its communicator
+    (dist.GradAllReducer.alloc_arena); a hook that declines (None) leaves the plain allocation."""
+    from vit_torch_b200 import functional as Fn
+    dev = torch.device("cpu")
+    mine = torch.zeros(128)
+    calls = []
+
+    def alloc(n, d):
+        calls.append((n, d))
+        return mine[:n]
+
+    arena = Fn.GradArena(100, dev, alloc=alloc)
+    assert calls == [(100, dev)] and arena.buf.data_ptr() == mine.data_ptr()
+    assert Fn.GradArena(100, dev, alloc=lambda n, d: None).buf.numel() == 100
+
+
+def test_default_data_parallel_mode():
+    from vit_torch_b200 import dist as vdist
+    assert [vdist.default_mode(n) for n in (1, 2, 4, 8)] == ["none", "split", "deferred", "deferred"]
+    # without a process group the reducer never asks NCCL for memory
+    m = torch.nn.Linear(4, 4)
+    red = vdist.GradAllReducer(m, overlap=False, register_arena=True)
+    assert red.alloc_arena(64, torch.device("cpu")) is None and not red.arena_registered

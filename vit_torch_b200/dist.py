@@ -47,6 +47,16 @@ def partition_limit(nccl_ctas: int) -> int:
     return max(n - int(nccl_ctas), n // 2)
 
 
+def default_mode(world: int) -> str:
+    """Data-parallel mode `bench.py --dp auto` (and a caller without a preference) should use for `world` GPUs of one
+    NVSwitch node. Measured on B200, ViT-B/16 bs128 per GPU (profiles/r02_summary.md section 4): the split-graph mode wins
+    at 2 GPUs (19.20 vs 19.36 ms/step) and loses at 8 (20.67 vs 20.10: its partitioned second graph costs more than the
+    hidden part of the all-reduce saves), so it is the default for 2 GPUs only."""
+    if world <= 1:
+        return "none"
+    return "split" if world == 2 else "deferred"
+
+
 class GradAllReducer:
     def __init__(self, model: torch.nn.Module, process_group=None, overlap: bool = True, compress: bool = False,
                  split: bool = False, split_ctas: int = 4, register_arena: bool = False):
