@@ -51,7 +51,10 @@ stat("-> first S issued (1->2)", 1, 2)
 stat("start -> first scores visible (0->24)", 0, 24)
 for j in range(nt):
     stat(f"tile {j}: elementwise (24+2j -> 25+2j)", 24 + 2 * j, 25 + 2 * j)
-    if which == "fwd" and j < 4:      # finer split of the forward's elementwise pass (warp 0) and the other group's span
+    if which == "fwd" and j == 1:     # skew between the eight softmax warps at the end of tile 1 (warp 0 = reference)
+        for w in range(1, 8):
+            stat(f"tile 1:   warp {w} done - warp 0 done", 27, 48 + w)
+    if which == "fwd" and j < 2:      # finer split of the forward's elementwise pass (warp 0) and the other group's span
         stat(f"tile {j}:   scores visible -> loaded, S released", 24 + 2 * j, 40 + 4 * j)
         stat(f"tile {j}:   -> max / rescale / P buffer free", 40 + 4 * j, 41 + 4 * j)
         stat(f"tile {j}:   -> exp, sums, pack, st.shared", 41 + 4 * j, 42 + 4 * j)

@@ -465,7 +465,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
             tc_fence_before_sync();
             mbar_arrive(s_free);
-            if (threadIdx.x == 0 && j < 4) VITK_TRACE_EV(a.trace, 40 + 4 * j);
+            if (threadIdx.x == 0 && j < 2) VITK_TRACE_EV(a.trace, 40 + 4 * j);
             if (work) {
                 float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                 if (nv == 32) {
@@ -502,7 +502,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 }
                 // P buffer (j & 1) was last read by PV_{j-2}
                 if (j >= 2) mbar_wait(&o_full[j & 1], ((j - 2) >> 1) & 1);
-                if (threadIdx.x == 0 && j < 4) VITK_TRACE_EV(a.trace, 41 + 4 * j);
+                if (threadIdx.x == 0 && j < 2) VITK_TRACE_EV(a.trace, 41 + 4 * j);
                 uint8_t* p_row = smem + AF2_SMEM_P + (j & 1) * AF_QTILE + row * 128;
                 float ps4[4] = {0.f, 0.f, 0.f, 0.f};
                 const float nm = -m_ref;
@@ -536,13 +536,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     }
                 }
                 l_run += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
-                if (threadIdx.x == 0 && j < 4) VITK_TRACE_EV(a.trace, 42 + 4 * j);
+                if (threadIdx.x == 0 && j < 2) VITK_TRACE_EV(a.trace, 42 + 4 * j);
                 fence_proxy_async_smem();
-                if (threadIdx.x == 0 && j < 4) VITK_TRACE_EV(a.trace, 43 + 4 * j);
+                if (threadIdx.x == 0 && j < 2) VITK_TRACE_EV(a.trace, 43 + 4 * j);
             }
             mbar_arrive(&p_full[2 * g + (j & 1)]);
             if (threadIdx.x == 0 && j < 8) VITK_TRACE_EV(a.trace, 25 + 2 * j);
             if (threadIdx.x == 128 && j < 4) VITK_TRACE_EV(a.trace, 17 + 2 * j);
+            if (lane == 0 && j == 1) VITK_TRACE_EV(a.trace, 48 + warp);      // every softmax warp: end of tile 1
         }
         // merge the two groups' partial softmax states, then each group writes half of the head's columns
         // (the Q tile is dead: its last reader, S of the last tile, completed before this group's last s_full wait)
